@@ -268,6 +268,24 @@ int moc_build_tracks(const Input *I, uint64_t seed, Params *out, uint64_t *rand_
 void moc_free_tracks(const Input *I, Params *P);
 double moc_time_per_intersection(const Input *I, double seconds);   /* src/utils.c:147-155 */
 
+/* Flat copies out of / into the pointer-rich host structures (tools and tests).
+ * `which` is a MOC_ARR_* id (same shapes as moc_get_array) or one of the host-only ids
+ * below.  Returns the number of bytes of the array; copies only if dst != NULL and
+ * bytes matches. */
+enum {
+    MOC_HOST_AZ_WEIGHT = 20,   /* float [T2]                    */
+    MOC_HOST_N_SEGMENTS = 21,  /* long  [T2]                    */
+    MOC_HOST_SEG_LENGTHS = 22, /* float [sum n_segments]        */
+    MOC_HOST_XS = 23,          /* float [N/8][G][3]             */
+    MOC_HOST_SCATTER = 24,     /* float [N/8][G][G]             */
+    MOC_HOST_XS_INDEX = 25,    /* int   [N]                     */
+    MOC_HOST_VOL = 26,         /* float [N]                     */
+    MOC_HOST_POLAR = 27,       /* float [P]                     */
+    MOC_HOST_TABLE = 28        /* float [2*expTable.N]          */
+};
+long moc_params_get(const Input *I, const Params *P, int which, void *dst, size_t bytes);
+long moc_params_set(const Input *I, Params *P, int which, const void *src, size_t bytes);
+
 #ifdef __cplusplus
 }
 #endif

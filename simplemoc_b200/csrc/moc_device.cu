@@ -1,0 +1,1397 @@
+/* moc_device.cu -- the C-ABI of libmoc_b200.so (include/moc_b200.h PART B1/B2):
+ * device mirrors of the reference's slabs, kernel launches, transfers.
+ *
+ * Data layout in HBM (one problem = one spatial domain = one GPU):
+ *   psi        float [T3][2][G]   the reference's flux slab verbatim (forward row, backward
+ *                                 row per 3D track, tracks.c:106-138) so the boundary exchange
+ *                                 can treat it as the flat array comms.c does
+ *   src slab   float fine_source[N][fai][G] | fine_flux[N][fai][G] | sigT[N][G]  (source.c:121-152)
+ *   xs         float [X][G][3],  scatter float [X][G][G],  xs_index int [N],  vol float [N]
+ *   tracks     SoA: p_weight[T3], z_height[T3] (unpacked on the device from the 40-byte AoS)
+ *   2D tracks  SoA: az_weight[T2], n_seg[T2], seg_start[T2+1], seg_len[S2]
+ *   sweep scratch: seg_count u32[T3], pair_count/pair_base u64[T2*P(+1)], and per batch
+ *                  track_off u32[tracks], rec_ds f32[], rec_zin f32[], rec_code u32[]
+ *
+ * There is no CPU implementation behind any entry point: without a usable CUDA device
+ * every compute call fails with MOC_ENODEVICE.
+ */
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <mutex>
+#include <unordered_map>
+#include <unordered_set>
+#include <vector>
+
+#include "moc_b200.h"
+#include "moc_internal.h"
+#include "moc_kernels.cuh"
+
+using namespace moc;
+
+// ------------------------------------------------------------------ small utilities
+
+#define CUDA_TRY(expr)                                                                        \
+    do {                                                                                      \
+        cudaError_t err__ = (expr);                                                           \
+        if (err__ != cudaSuccess) {                                                           \
+            moc_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(err__), __FILE__, \
+                          __LINE__);                                                          \
+            return err__ == cudaErrorMemoryAllocation ? MOC_ENOMEM : MOC_ECUDA;               \
+        }                                                                                     \
+    } while (0)
+
+static int usable_devices()
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+extern "C" int moc_device_count(void) { return usable_devices(); }
+
+static std::mutex g_pin_mutex;
+static std::unordered_set<void *> g_pinned;
+
+extern "C" void *moc_host_alloc(size_t bytes)
+{
+    if (bytes == 0) bytes = 1;
+    if (usable_devices() > 0) {
+        void *p = nullptr;
+        if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) == cudaSuccess) {
+            memset(p, 0, bytes);
+            std::lock_guard<std::mutex> lock(g_pin_mutex);
+            g_pinned.insert(p);
+            return p;
+        }
+        cudaGetLastError();
+    }
+    return calloc(1, bytes);
+}
+
+extern "C" void moc_host_free(void *p)
+{
+    if (!p) return;
+    bool pinned = false;
+    {
+        std::lock_guard<std::mutex> lock(g_pin_mutex);
+        pinned = g_pinned.erase(p) > 0;
+    }
+    if (pinned) cudaFreeHost(p);
+    else free(p);
+}
+
+// ------------------------------------------------------------------ the handle
+
+struct DeviceBuffers {
+    // 2D tracks
+    float *az_weight = nullptr;
+    int *n_seg = nullptr;
+    long long *seg_start = nullptr;
+    float *seg_len = nullptr;
+    // polar
+    double *cos_p = nullptr, *sin_p = nullptr;
+    float *mu = nullptr;
+    // 3D tracks
+    float *p_weight = nullptr, *z_height = nullptr, *psi = nullptr;
+    TrackImage *track_image = nullptr;   // only for the drop-in path
+    // sources
+    float *src = nullptr, *xs = nullptr, *scatter = nullptr, *vol = nullptr, *table = nullptr;
+    int *xs_index = nullptr;
+    // sweep scratch
+    uint32_t *seg_count = nullptr, *track_off = nullptr, *rec_code = nullptr;
+    unsigned long long *pair_count = nullptr, *pair_base = nullptr, *digest = nullptr;
+    float *rec_ds = nullptr, *rec_zin = nullptr;
+    // reductions
+    float *per_region_a = nullptr, *per_region_b = nullptr, *per_fine = nullptr, *scalars = nullptr;
+    float *leakage = nullptr;
+};
+
+struct moc_handle {
+    int device = 0;
+    Input I;
+    long long T2 = 0, T3 = 0, N = 0, X = 0, S2 = 0;
+    int P = 0, Z = 0, G = 0, F = 0;
+    Table table_host;              // values pointer owned by the caller's Params; copied
+    float table_dx = 0, table_max = 0;
+    int table_n = 0;
+    DeviceBuffers d;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[8] = {};
+    // options
+    int exp_mode = 0;
+    unsigned long long seed = 1, rand_base = 0;
+    long long batch_segments = 0;  // 0 = choose from free memory
+    int source_stride = 48;
+    int lanes_override = 0;
+    int want_digest = 0;
+    // scratch capacity
+    long long rec_capacity = 0, off_capacity = 0;
+    std::vector<unsigned long long> pair_base_host;
+    unsigned long long *pair_base_pinned = nullptr;
+    moc_sweep_timing timing;
+    float leakage_host = 0.f;
+    // comms
+    void *nccl_comm = nullptr;
+    int nranks = 1, rank = 0;
+    float *recv_stage = nullptr;
+    cudaStream_t comm_stream = nullptr;
+};
+
+static int require_device(int device)
+{
+    const int n = usable_devices();
+    if (n <= 0) {
+        moc_set_error("no usable CUDA device: libmoc_b200 has no CPU fallback");
+        return MOC_ENODEVICE;
+    }
+    if (device < 0 || device >= n) {
+        moc_set_error("device %d out of range (%d visible)", device, n);
+        return MOC_EINVAL;
+    }
+    return MOC_OK;
+}
+
+template <class T>
+static int dev_alloc(T **p, size_t count)
+{
+    CUDA_TRY(cudaMalloc((void **)p, std::max<size_t>(count, 1) * sizeof(T)));
+    return MOC_OK;
+}
+
+static void free_buffers(DeviceBuffers &d)
+{
+    void *all[] = {d.az_weight, d.n_seg, d.seg_start, d.seg_len, d.cos_p, d.sin_p, d.mu, d.p_weight,
+                   d.z_height, d.psi, d.track_image, d.src, d.xs, d.scatter, d.vol, d.table,
+                   d.xs_index, d.seg_count, d.track_off, d.rec_code, d.pair_count, d.pair_base,
+                   d.digest, d.rec_ds, d.rec_zin, d.per_region_a, d.per_region_b, d.per_fine,
+                   d.scalars, d.leakage};
+    for (void *p : all)
+        if (p) cudaFree(p);
+    d = DeviceBuffers();
+}
+
+// ------------------------------------------------------------------ host layout checks
+
+// The reference stores everything in a handful of contiguous slabs and hands out
+// pointer-rich views.  The device mirror is built from the slabs;
+// these checks make sure the host Params really has that shape.
+struct HostLayout {
+    const Track *tracks;      // [T3]
+    float *psi;               // [T3][2][G]
+    float *src;               // source slab
+    float *xs, *scatter;      // material slabs
+    std::vector<int> xs_index;
+    std::vector<float> vol;
+};
+
+static inline const Source *source_at(const Params *P, long long i, int stride)
+{
+    return reinterpret_cast<const Source *>(reinterpret_cast<const char *>(P->sources) + (size_t)i * stride);
+}
+
+static int inspect_layout(const Input *I, const Params *P, int source_stride, HostLayout &L)
+{
+    const long long T2 = I->ntracks_2D, T3 = I->ntracks, N = I->n_source_regions_per_node;
+    const int Pn = I->n_polar_angles, Z = I->z_stacked, G = I->n_egroups, F = I->fai;
+    if (!P->tracks || !P->tracks_2D || !P->sources || !P->polar_angles || !P->expTable.values) {
+        moc_set_error("Params has null members");
+        return MOC_EINVAL;
+    }
+    L.tracks = P->tracks[0][0];
+    for (long long i = 0; i < T2; i++)
+        for (int j = 0; j < Pn; j++)
+            if (P->tracks[i][j] != L.tracks + (i * Pn + j) * Z) {
+                moc_set_error("tracks[%lld][%d] is not inside one contiguous [T2][P][Z] Track array "
+                              "(reference tracks.c:87-104)", i, j);
+                return MOC_ELAYOUT;
+            }
+    L.psi = L.tracks[0].f_psi;
+    const long long probe[3] = {0, T3 / 2, T3 - 1};
+    for (long long t : probe)
+        if (L.tracks[t].f_psi != L.psi + 2 * t * G || L.tracks[t].b_psi != L.psi + (2 * t + 1) * G) {
+            moc_set_error("angular flux of track %lld is not at [t][2][G] in one slab "
+                          "(reference tracks.c:106-138)", t);
+            return MOC_ELAYOUT;
+        }
+    const Source *s0 = source_at(P, 0, source_stride);
+    L.src = s0->fine_source[0];
+    L.xs = s0->XS[0];
+    L.scatter = s0->scattering_matrix[0];
+    L.xs_index.resize((size_t)N);
+    L.vol.resize((size_t)N);
+    const long long X = N / 8;
+    for (long long i = 0; i < N; i++) {
+        const Source *s = source_at(P, i, source_stride);
+        if (s->fine_source[0] != L.src + i * F * G || s->fine_flux[0] != L.src + (N + i) * F * G ||
+            s->sigT != L.src + 2 * N * F * G + i * G ||
+            (F > 1 && s->fine_source[1] != s->fine_source[0] + G)) {
+            moc_set_error("source region %lld does not view the source|flux|sigT slab "
+                          "(reference source.c:121-152); OPENMP builds need MOC_OPT_SOURCE_STRIDE=56", i);
+            return MOC_ELAYOUT;
+        }
+        const long long m = (s->XS[0] - L.xs) / (3 * G);
+        const long long m2 = (s->scattering_matrix[0] - L.scatter) / ((long long)G * G);
+        if (m < 0 || m >= X || m != m2 || s->XS[0] != L.xs + m * 3 * G) {
+            moc_set_error("source region %lld: material pointers are not rows of the XS/scattering "
+                          "slabs (reference source.c:31-86,183-193)", i);
+            return MOC_ELAYOUT;
+        }
+        L.xs_index[(size_t)i] = (int)m;
+        L.vol[(size_t)i] = s->vol;
+    }
+    return MOC_OK;
+}
+
+// ------------------------------------------------------------------ create / destroy
+
+static int upload_static(moc_handle *h, const Params *P, const HostLayout &L)
+{
+    const long long T2 = h->T2;
+    const int Pn = h->P, G = h->G;
+    // 2D tracks -> SoA
+    std::vector<float> az((size_t)T2);
+    std::vector<int> ns((size_t)T2);
+    std::vector<long long> start((size_t)T2 + 1);
+    long long total = 0;
+    for (long long i = 0; i < T2; i++) {
+        az[(size_t)i] = P->tracks_2D[i].az_weight;
+        const long n = P->tracks_2D[i].n_segments;
+        ns[(size_t)i] = (int)(n > 0 ? n : 0);
+        start[(size_t)i] = total;
+        total += ns[(size_t)i];
+    }
+    start[(size_t)T2] = total;
+    h->S2 = total;
+    std::vector<float> len((size_t)std::max<long long>(total, 1));
+    for (long long i = 0; i < T2; i++)
+        for (int n = 0; n < ns[(size_t)i]; n++)
+            len[(size_t)(start[(size_t)i] + n)] = P->tracks_2D[i].segments[n].length;
+    int rc;
+    if ((rc = dev_alloc(&h->d.az_weight, (size_t)T2))) return rc;
+    if ((rc = dev_alloc(&h->d.n_seg, (size_t)T2))) return rc;
+    if ((rc = dev_alloc(&h->d.seg_start, (size_t)T2 + 1))) return rc;
+    if ((rc = dev_alloc(&h->d.seg_len, (size_t)total))) return rc;
+    CUDA_TRY(cudaMemcpy(h->d.az_weight, az.data(), sizeof(float) * (size_t)T2, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(h->d.n_seg, ns.data(), sizeof(int) * (size_t)T2, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(h->d.seg_start, start.data(), sizeof(long long) * ((size_t)T2 + 1), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(h->d.seg_len, len.data(), sizeof(float) * (size_t)total, cudaMemcpyHostToDevice));
+
+    // polar angles: the reference evaluates cos()/sin() of the float angle in double
+    // (solver.c:373,383,417,449); do it here with the same libm and ship the doubles.
+    std::vector<double> c((size_t)Pn), s((size_t)Pn);
+    std::vector<float> mu((size_t)Pn);
+    for (int j = 0; j < Pn; j++) {
+        const float ang = P->polar_angles[j];
+        // explicit widening: in C++ cos(float) would pick the float overload, the reference is C
+        c[(size_t)j] = cos((double)ang);
+        s[(size_t)j] = sin((double)ang);
+        mu[(size_t)j] = (float)cos((double)ang);
+    }
+    if ((rc = dev_alloc(&h->d.cos_p, (size_t)Pn))) return rc;
+    if ((rc = dev_alloc(&h->d.sin_p, (size_t)Pn))) return rc;
+    if ((rc = dev_alloc(&h->d.mu, (size_t)Pn))) return rc;
+    CUDA_TRY(cudaMemcpy(h->d.cos_p, c.data(), sizeof(double) * (size_t)Pn, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(h->d.sin_p, s.data(), sizeof(double) * (size_t)Pn, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(h->d.mu, mu.data(), sizeof(float) * (size_t)Pn, cudaMemcpyHostToDevice));
+
+    // materials
+    if ((rc = dev_alloc(&h->d.xs, (size_t)h->X * G * 3))) return rc;
+    if ((rc = dev_alloc(&h->d.scatter, (size_t)h->X * G * G))) return rc;
+    if ((rc = dev_alloc(&h->d.xs_index, (size_t)h->N))) return rc;
+    if ((rc = dev_alloc(&h->d.vol, (size_t)h->N))) return rc;
+    CUDA_TRY(cudaMemcpy(h->d.xs, L.xs, sizeof(float) * (size_t)h->X * G * 3, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(h->d.scatter, L.scatter, sizeof(float) * (size_t)h->X * G * G, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(h->d.xs_index, L.xs_index.data(), sizeof(int) * (size_t)h->N, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(h->d.vol, L.vol.data(), sizeof(float) * (size_t)h->N, cudaMemcpyHostToDevice));
+
+    // exponential table (utils.c:48-78), as built by the caller
+    h->table_dx = P->expTable.dx;
+    h->table_max = P->expTable.maxVal;
+    h->table_n = P->expTable.N;
+    if ((rc = dev_alloc(&h->d.table, (size_t)2 * h->table_n))) return rc;
+    CUDA_TRY(cudaMemcpy(h->d.table, P->expTable.values, sizeof(float) * 2 * (size_t)h->table_n, cudaMemcpyHostToDevice));
+    return MOC_OK;
+}
+
+static int upload_mutable(moc_handle *h, const HostLayout &L, bool with_backward_psi)
+{
+    const size_t T3 = (size_t)h->T3, G = (size_t)h->G;
+    // Track AoS image -> SoA on the device
+    CUDA_TRY(cudaMemcpyAsync(h->d.track_image, L.tracks, sizeof(TrackImage) * T3, cudaMemcpyHostToDevice, h->stream));
+    const int threads = 256;
+    unpack_tracks_kernel<<<(unsigned)((T3 + threads - 1) / threads), threads, 0, h->stream>>>(
+        h->d.track_image, (long long)T3, h->d.p_weight, h->d.z_height);
+    if (with_backward_psi) {
+        CUDA_TRY(cudaMemcpyAsync(h->d.psi, L.psi, sizeof(float) * 2 * T3 * G, cudaMemcpyHostToDevice, h->stream));
+    } else {
+        // forward rows only: row pitch 2*G floats
+        CUDA_TRY(cudaMemcpy2DAsync(h->d.psi, sizeof(float) * 2 * G, L.psi, sizeof(float) * 2 * G,
+                                   sizeof(float) * G, T3, cudaMemcpyHostToDevice, h->stream));
+    }
+    CUDA_TRY(cudaMemcpyAsync(h->d.src, L.src, sizeof(float) * (size_t)(2 * h->F + 1) * (size_t)h->N * G,
+                             cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaGetLastError());
+    return MOC_OK;
+}
+
+extern "C" int moc_destroy(moc_handle *h)
+{
+    if (!h) return MOC_OK;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    free_buffers(h->d);
+    for (auto &e : h->ev)
+        if (e) cudaEventDestroy(e);
+    if (h->pair_base_pinned) cudaFreeHost(h->pair_base_pinned);
+    if (h->recv_stage) cudaFree(h->recv_stage);
+    if (h->comm_stream) cudaStreamDestroy(h->comm_stream);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return MOC_OK;
+}
+
+static int create_common(const Input *I, const Params *P, int device, int source_stride, moc_handle **out,
+                         HostLayout &L)
+{
+    int rc = require_device(device);
+    if (rc) return rc;
+    if (I->axial_exp != 0 && I->axial_exp != 2) {
+        // the reference prints this and exit(1)s from inside the sweep (solver.c:506-511)
+        moc_set_error("Error: invalid axial expansion order %d. Please input 0 or 2", I->axial_exp);
+        return MOC_EINVAL;
+    }
+    if (I->axial_exp == 2 && I->fai < 3) {
+        moc_set_error("axial_exp=2 needs fai >= 3 (the edge stencil of solver.c:55-112 reads three rows)");
+        return MOC_EINVAL;
+    }
+    if (I->fai > 63 || I->n_source_regions_per_node >= (1 << 24) || I->z_stacked > 16384) {
+        moc_set_error("unsupported size: fai=%d (max 63), N=%ld (max 2^24-1), z_stacked=%d (max 16384)",
+                      I->fai, I->n_source_regions_per_node, I->z_stacked);
+        return MOC_EINVAL;
+    }
+    if ((rc = inspect_layout(I, P, source_stride, L))) return rc;
+    CUDA_TRY(cudaSetDevice(device));
+    moc_handle *h = new moc_handle();
+    h->device = device;
+    h->I = *I;
+    h->T2 = I->ntracks_2D;
+    h->T3 = I->ntracks;
+    h->N = I->n_source_regions_per_node;
+    h->X = h->N / 8;
+    h->P = I->n_polar_angles;
+    h->Z = I->z_stacked;
+    h->G = I->n_egroups;
+    h->F = I->fai;
+    h->source_stride = source_stride;
+    memset(&h->timing, 0, sizeof h->timing);
+    auto fail = [&](int code) {
+        moc_destroy(h);
+        return code;
+    };
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        moc_set_error("cudaStreamCreate failed");
+        return fail(MOC_ECUDA);
+    }
+    for (auto &e : h->ev)
+        if (cudaEventCreate(&e) != cudaSuccess) {
+            moc_set_error("cudaEventCreate failed");
+            return fail(MOC_ECUDA);
+        }
+    if ((rc = upload_static(h, P, L))) return fail(rc);
+    const size_t T3 = (size_t)h->T3, G = (size_t)h->G, N = (size_t)h->N, F = (size_t)h->F;
+    const size_t pairs = (size_t)h->T2 * h->P;
+    if ((rc = dev_alloc(&h->d.track_image, T3))) return fail(rc);
+    if ((rc = dev_alloc(&h->d.p_weight, T3))) return fail(rc);
+    if ((rc = dev_alloc(&h->d.z_height, T3))) return fail(rc);
+    if ((rc = dev_alloc(&h->d.psi, 2 * T3 * G))) return fail(rc);
+    if ((rc = dev_alloc(&h->d.src, (2 * F + 1) * N * G))) return fail(rc);
+    if ((rc = dev_alloc(&h->d.seg_count, T3))) return fail(rc);
+    if ((rc = dev_alloc(&h->d.pair_count, pairs))) return fail(rc);
+    if ((rc = dev_alloc(&h->d.pair_base, pairs + 1))) return fail(rc);
+    if ((rc = dev_alloc(&h->d.digest, 4))) return fail(rc);
+    if ((rc = dev_alloc(&h->d.per_region_a, N))) return fail(rc);
+    if ((rc = dev_alloc(&h->d.per_region_b, N))) return fail(rc);
+    if ((rc = dev_alloc(&h->d.per_fine, N * F))) return fail(rc);
+    if ((rc = dev_alloc(&h->d.scalars, 8))) return fail(rc);
+    if ((rc = dev_alloc(&h->d.leakage, 1))) return fail(rc);
+    if (cudaHostAlloc((void **)&h->pair_base_pinned, sizeof(unsigned long long) * (pairs + 1), cudaHostAllocDefault) != cudaSuccess) {
+        moc_set_error("cudaHostAlloc(pair_base) failed");
+        return fail(MOC_ENOMEM);
+    }
+    cudaMemsetAsync(h->d.seg_count, 0, sizeof(uint32_t) * T3, h->stream);
+    cudaMemsetAsync(h->d.digest, 0, sizeof(unsigned long long) * 4, h->stream);
+    cudaMemsetAsync(h->d.scalars, 0, sizeof(float) * 8, h->stream);
+    h->leakage_host = P->leakage ? *P->leakage : 0.f;
+    cudaMemcpyAsync(h->d.leakage, &h->leakage_host, sizeof(float), cudaMemcpyHostToDevice, h->stream);
+    *out = h;
+    return MOC_OK;
+}
+
+extern "C" int moc_create(const Input *I, const Params *P, int device, moc_handle **out)
+{
+    if (!I || !P || !out) {
+        moc_set_error("moc_create: null argument");
+        return MOC_EINVAL;
+    }
+    HostLayout L;
+    int rc = create_common(I, P, device, 48, out, L);
+    if (rc) return rc;
+    moc_handle *h = *out;
+    if ((rc = upload_mutable(h, L, true))) {
+        moc_destroy(h);
+        *out = nullptr;
+        return rc;
+    }
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return MOC_OK;
+}
+
+extern "C" int moc_set_option(moc_handle *h, int option, long value)
+{
+    if (!h) return MOC_EINVAL;
+    switch (option) {
+    case MOC_OPT_EXP_MODE:
+        if (value != 0 && value != 1) break;
+        h->exp_mode = (int)value;
+        return MOC_OK;
+    case MOC_OPT_SEED: h->seed = (unsigned long long)value; return MOC_OK;
+    case MOC_OPT_RAND_BASE: h->rand_base = (unsigned long long)value; return MOC_OK;
+    case MOC_OPT_BATCH_SEGMENTS:
+        if (value < 0) break;
+        h->batch_segments = value;
+        return MOC_OK;
+    case MOC_OPT_SOURCE_STRIDE:
+        if (value != 48 && value != 56) break;
+        h->source_stride = (int)value;
+        return MOC_OK;
+    case MOC_OPT_LANES_PER_TRACK:
+        if (value != 0 && value != 4 && value != 8 && value != 16 && value != 32) break;
+        h->lanes_override = (int)value;
+        return MOC_OK;
+    case 100: h->want_digest = value != 0; return MOC_OK;   // MOC_OPT_DIGEST (diagnostic)
+    }
+    moc_set_error("moc_set_option: bad option %d / value %ld", option, value);
+    return MOC_EINVAL;
+}
+
+extern "C" long moc_get_option(moc_handle *h, int option)
+{
+    if (!h) return -1;
+    switch (option) {
+    case MOC_OPT_EXP_MODE: return h->exp_mode;
+    case MOC_OPT_SEED: return (long)h->seed;
+    case MOC_OPT_RAND_BASE: return (long)h->rand_base;
+    case MOC_OPT_BATCH_SEGMENTS: return (long)h->batch_segments;
+    case MOC_OPT_SOURCE_STRIDE: return h->source_stride;
+    case MOC_OPT_LANES_PER_TRACK: return h->lanes_override;
+    case 100: return h->want_digest;
+    }
+    return -1;
+}
+
+// ------------------------------------------------------------------ the sweep
+
+static WalkParams walk_params(const moc_handle *h)
+{
+    WalkParams w;
+    memset(&w, 0, sizeof w);
+    const Input &I = h->I;
+    w.seg_len = h->d.seg_len;
+    w.seg_start = h->d.seg_start;
+    w.n_seg = h->d.n_seg;
+    w.cos_p = h->d.cos_p;
+    w.sin_p = h->d.sin_p;
+    w.z_height = h->d.z_height;
+    w.seg_count = h->d.seg_count;
+    w.pair_count = h->d.pair_count;
+    w.pair_base = h->d.pair_base;
+    w.rec_ds = h->d.rec_ds;
+    w.rec_zin = h->d.rec_zin;
+    w.rec_code = h->d.rec_code;
+    w.track_off = h->d.track_off;
+    w.digest = h->want_digest ? h->d.digest : nullptr;
+    w.P = h->P;
+    w.Z = h->Z;
+    w.fai = h->F;
+    w.axial_exp = I.axial_exp;
+    w.n_regions = (unsigned int)h->N;
+    w.z_sep = I.axial_z_sep;
+    // solver.c:288-289: float / int, widened; then double / int
+    const double node_dz = (double)(float)(I.height / I.decomp_assemblies_ax);
+    const double fine_dz = node_dz / (I.cai * I.fai);
+    w.node_dz = node_dz;
+    w.fine_dz = fine_dz;
+    w.dz_interval = (float)fine_dz;
+    // solver.c:38: float / int
+    w.dz_fine = I.height / (I.fai * I.decomp_assemblies_ax * I.cai);
+    w.seed = h->seed;
+    w.rand_base = h->rand_base;
+    return w;
+}
+
+template <bool FILL>
+static void launch_walk(const moc_handle *h, const WalkParams &w, long long n_pairs)
+{
+    if (n_pairs <= 0) return;
+    const int Z = h->Z;
+    int kpt = 1;
+    while (kpt < 16 && (Z + kpt - 1) / kpt > 256) kpt *= 2;
+    int threads = ((Z + kpt - 1) / kpt + 31) / 32 * 32;
+    if (threads > 1024) threads = 1024;
+    const unsigned grid = (unsigned)n_pairs;
+    switch (kpt) {
+    case 1: stack_walk_kernel<1, FILL><<<grid, threads, 0, h->stream>>>(w); break;
+    case 2: stack_walk_kernel<2, FILL><<<grid, threads, 0, h->stream>>>(w); break;
+    case 4: stack_walk_kernel<4, FILL><<<grid, threads, 0, h->stream>>>(w); break;
+    case 8: stack_walk_kernel<8, FILL><<<grid, threads, 0, h->stream>>>(w); break;
+    default: stack_walk_kernel<16, FILL><<<grid, threads, 0, h->stream>>>(w); break;
+    }
+}
+
+// lane mapping of the attenuation kernel for G groups
+struct LaneMap {
+    int L, NV4, NS;
+};
+static LaneMap choose_lanes(int G, int lanes_override)
+{
+    if (lanes_override == 0) {
+        if (G % 4 == 0) {
+            if (G == 104 || G == 100) return {8, 3, 1};
+            if (G == 128) return {8, 4, 0};
+            if (G == 96) return {8, 3, 0};
+            if (G == 64) return {8, 2, 0};
+            if (G == 32) return {8, 1, 0};
+            if (G == 16) return {4, 1, 0};
+        }
+    } else if (lanes_override == 32 && G % 4 == 0 && G <= 128) {
+        return {32, 1, 0};
+    } else if (lanes_override == 16 && G % 4 == 0 && G <= 128) {
+        return {16, 2, 0};
+    }
+    // generic: single groups only
+    const int L = (lanes_override == 32 || G > 128) ? 32 : 8;
+    int ns = (G + L - 1) / L;
+    int r = 1;
+    while (r < ns) r *= 2;
+    return {L, 0, r};
+}
+
+template <int L, int NV4, int NS>
+static int launch_attenuate_mode(const moc_handle *h, const AttenuateParams &a, unsigned grid, size_t smem)
+{
+    const bool sfu = h->exp_mode == 1, flat = h->I.axial_exp == 0;
+    if (!sfu && !flat) attenuate_kernel<L, NV4, NS, false, false><<<grid, 128, smem, h->stream>>>(a);
+    else if (sfu && !flat) attenuate_kernel<L, NV4, NS, true, false><<<grid, 128, 0, h->stream>>>(a);
+    else if (!sfu && flat) attenuate_kernel<L, NV4, NS, false, true><<<grid, 128, smem, h->stream>>>(a);
+    else attenuate_kernel<L, NV4, NS, true, true><<<grid, 128, 0, h->stream>>>(a);
+    return MOC_OK;
+}
+
+static int launch_attenuate(const moc_handle *h, const AttenuateParams &a, long long n_tracks)
+{
+    if (n_tracks <= 0) return MOC_OK;
+    const LaneMap m = choose_lanes(h->G, h->lanes_override);
+    if (4 * m.L * m.NV4 + m.L * m.NS < h->G) {
+        moc_set_error("no lane mapping for %d energy groups", h->G);
+        return MOC_EINVAL;
+    }
+    const int tracks_per_block = 4 * (32 / m.L);
+    const unsigned grid = (unsigned)((n_tracks + tracks_per_block - 1) / tracks_per_block);
+    const size_t smem = sizeof(float2) * (size_t)h->table_n;
+#define MOC_CASE(l, v, s) \
+    if (m.L == l && m.NV4 == v && m.NS == s) return launch_attenuate_mode<l, v, s>(h, a, grid, smem);
+    MOC_CASE(8, 3, 1)
+    MOC_CASE(8, 4, 0)
+    MOC_CASE(8, 3, 0)
+    MOC_CASE(8, 2, 0)
+    MOC_CASE(8, 1, 0)
+    MOC_CASE(4, 1, 0)
+    MOC_CASE(32, 1, 0)
+    MOC_CASE(16, 2, 0)
+    MOC_CASE(8, 0, 1)
+    MOC_CASE(8, 0, 2)
+    MOC_CASE(8, 0, 4)
+    MOC_CASE(8, 0, 8)
+    MOC_CASE(8, 0, 16)
+    MOC_CASE(32, 0, 1)
+    MOC_CASE(32, 0, 2)
+    MOC_CASE(32, 0, 4)
+    MOC_CASE(32, 0, 8)
+    MOC_CASE(32, 0, 16)
+#undef MOC_CASE
+    moc_set_error("no attenuation kernel instantiated for lane map L=%d NV4=%d NS=%d", m.L, m.NV4, m.NS);
+    return MOC_EINVAL;
+}
+
+static int ensure_record_capacity(moc_handle *h, long long records, long long tracks)
+{
+    if (records > h->rec_capacity) {
+        if (h->d.rec_ds) cudaFree(h->d.rec_ds);
+        if (h->d.rec_zin) cudaFree(h->d.rec_zin);
+        if (h->d.rec_code) cudaFree(h->d.rec_code);
+        h->d.rec_ds = h->d.rec_zin = nullptr;
+        h->d.rec_code = nullptr;
+        h->rec_capacity = 0;
+        int rc;
+        if ((rc = dev_alloc(&h->d.rec_ds, (size_t)records))) return rc;
+        if ((rc = dev_alloc(&h->d.rec_zin, (size_t)records))) return rc;
+        if ((rc = dev_alloc(&h->d.rec_code, (size_t)records))) return rc;
+        h->rec_capacity = records;
+    }
+    if (tracks > h->off_capacity) {
+        if (h->d.track_off) cudaFree(h->d.track_off);
+        h->d.track_off = nullptr;
+        h->off_capacity = 0;
+        int rc;
+        if ((rc = dev_alloc(&h->d.track_off, (size_t)tracks))) return rc;
+        h->off_capacity = tracks;
+    }
+    return MOC_OK;
+}
+
+extern "C" int moc_sweep(moc_handle *h, long *segments_processed)
+{
+    if (!h) {
+        moc_set_error("moc_sweep: null handle");
+        return MOC_EINVAL;
+    }
+    CUDA_TRY(cudaSetDevice(h->device));
+    const long long pairs = h->T2 * h->P;
+    cudaEvent_t e_start = h->ev[0], e_count = h->ev[1], e_scan = h->ev[2], e_end = h->ev[3];
+    long launches = 0;
+
+    // ---- pass 1: segment counts per ray and per (2D track, polar angle) stack
+    WalkParams w = walk_params(h);
+    CUDA_TRY(cudaEventRecord(e_start, h->stream));
+    if (h->want_digest) cudaMemsetAsync(h->d.digest, 0, sizeof(unsigned long long) * 4, h->stream);
+    launch_walk<false>(h, w, pairs);
+    launches++;
+    CUDA_TRY(cudaEventRecord(e_count, h->stream));
+    pair_scan_kernel<<<1, 1024, 0, h->stream>>>(h->d.pair_count, h->d.pair_base, pairs);
+    launches++;
+    CUDA_TRY(cudaMemcpyAsync(h->pair_base_pinned, h->d.pair_base, sizeof(unsigned long long) * (size_t)(pairs + 1),
+                             cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaEventRecord(e_scan, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    CUDA_TRY(cudaGetLastError());
+    const unsigned long long *base = h->pair_base_pinned;
+    const unsigned long long total = base[pairs];
+
+    // ---- batches of whole stacks whose records fit the staging buffers
+    long long cap = h->batch_segments;
+    if (cap <= 0) {
+        size_t free_b = 0, total_b = 0;
+        CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+        free_b += (size_t)h->rec_capacity * 12;   // what we already hold can be reused
+        cap = (long long)((double)free_b * 0.7 / 12.0);
+        if (cap > (1ll << 31)) cap = 1ll << 31;
+    }
+    unsigned long long largest_pair = 0;
+    for (long long p = 0; p < pairs; p++) largest_pair = std::max(largest_pair, base[p + 1] - base[p]);
+    if ((unsigned long long)cap < largest_pair) cap = (long long)largest_pair;
+    if (cap >= (1ll << 32)) cap = (1ll << 32) - 1;
+    if (largest_pair >= (1ull << 32)) {
+        moc_set_error("a single z-stack produces %llu segments (> 2^32)", largest_pair);
+        return MOC_EINVAL;
+    }
+    const long long need = (long long)std::min<unsigned long long>(total, (unsigned long long)cap);
+    // the largest batch in tracks
+    std::vector<std::pair<long long, long long>> batches;
+    {
+        long long p = 0;
+        while (p < pairs) {
+            long long q = p;
+            const unsigned long long lim = base[p] + (unsigned long long)cap;
+            // largest q with base[q] <= lim
+            q = (long long)(std::upper_bound(base + p, base + pairs + 1, lim) - base) - 1;
+            if (q <= p) q = p + 1;
+            batches.emplace_back(p, q);
+            p = q;
+        }
+    }
+    long long max_tracks = 0;
+    for (auto &b : batches) max_tracks = std::max(max_tracks, (b.second - b.first) * (long long)h->Z);
+    int rc = ensure_record_capacity(h, std::max<long long>(need, 1), std::max<long long>(max_tracks, 1));
+    if (rc) return rc;
+    w = walk_params(h);   // record pointers may have changed
+
+    AttenuateParams a;
+    memset(&a, 0, sizeof a);
+    a.rec_ds = h->d.rec_ds;
+    a.rec_zin = h->d.rec_zin;
+    a.rec_code = h->d.rec_code;
+    a.track_off = h->d.track_off;
+    a.seg_count = h->d.seg_count;
+    a.p_weight = h->d.p_weight;
+    a.az_weight = h->d.az_weight;
+    a.mu = h->d.mu;
+    a.psi = h->d.psi;
+    a.fine_source = h->d.src;
+    a.fine_flux = h->d.src + (size_t)h->N * h->F * h->G;
+    a.sigT = h->d.src + (size_t)2 * h->N * h->F * h->G;
+    a.table = h->d.table;
+    a.table_dx = h->table_dx;
+    a.table_max = h->table_max;
+    a.table_half_dx = 0.5f * h->table_dx;
+    a.table_n = h->table_n;
+    a.P = h->P;
+    a.Z = h->Z;
+    a.G = h->G;
+    a.fai = h->F;
+    {
+        const float dz = w.dz_fine;
+        a.inv_2dz = 1.0f / (2.f * dz);
+        a.inv_2dz2 = 1.0f / (2.f * dz * dz);
+    }
+
+    float fill_ms = 0.f, att_ms = 0.f;
+    cudaEvent_t b0 = h->ev[4], b1 = h->ev[5], b2 = h->ev[6];
+    for (auto &b : batches) {
+        w.first_pair = b.first;
+        w.batch_first_record = base[b.first];
+        CUDA_TRY(cudaEventRecord(b0, h->stream));
+        launch_walk<true>(h, w, b.second - b.first);
+        launches++;
+        CUDA_TRY(cudaEventRecord(b1, h->stream));
+        a.first_track = b.first * h->Z;
+        a.end_track = b.second * h->Z;
+        if ((rc = launch_attenuate(h, a, a.end_track - a.first_track))) return rc;
+        launches++;
+        CUDA_TRY(cudaEventRecord(b2, h->stream));
+        if (batches.size() > 1) {
+            // per-batch times need the events before they are re-recorded
+            CUDA_TRY(cudaEventSynchronize(b2));
+            float f = 0, t = 0;
+            cudaEventElapsedTime(&f, b0, b1);
+            cudaEventElapsedTime(&t, b1, b2);
+            fill_ms += f;
+            att_ms += t;
+        }
+    }
+    CUDA_TRY(cudaEventRecord(e_end, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    CUDA_TRY(cudaGetLastError());
+    if (batches.size() == 1) {
+        cudaEventElapsedTime(&fill_ms, b0, b1);
+        cudaEventElapsedTime(&att_ms, b1, b2);
+    }
+    cudaEventElapsedTime(&h->timing.count_ms, e_start, e_count);
+    cudaEventElapsedTime(&h->timing.scan_ms, e_count, e_scan);
+    cudaEventElapsedTime(&h->timing.total_ms, e_start, e_end);
+    h->timing.fill_ms = fill_ms;
+    h->timing.attenuate_ms = att_ms;
+    h->timing.n_batches = (long)batches.size();
+    h->timing.launches = launches;
+    h->I.segments_processed = (long)total;
+    h->rand_base += total;   // the serial rand() stream moves on by one draw per segment (solver.c:481)
+    if (segments_processed) *segments_processed = (long)total;
+    return MOC_OK;
+}
+
+extern "C" int moc_get_sweep_timing(moc_handle *h, moc_sweep_timing *t)
+{
+    if (!h || !t) return MOC_EINVAL;
+    *t = h->timing;
+    return MOC_OK;
+}
+
+// ------------------------------------------------------------------ reductions
+
+static SourceParams source_params(const moc_handle *h)
+{
+    SourceParams p;
+    p.fine_source = h->d.src;
+    p.fine_flux = h->d.src + (size_t)h->N * h->F * h->G;
+    p.xs = h->d.xs;
+    p.scatter = h->d.scatter;
+    p.xs_index = h->d.xs_index;
+    p.vol = h->d.vol;
+    p.N = h->N;
+    p.G = h->G;
+    p.fai = h->F;
+    return p;
+}
+
+static int allreduce_scalars(moc_handle *h, float *dev, int count);   // comms section
+
+extern "C" int moc_renormalize(moc_handle *h)
+{
+    if (!h) return MOC_EINVAL;
+    CUDA_TRY(cudaSetDevice(h->device));
+    const SourceParams p = source_params(h);
+    const unsigned rb = (unsigned)((h->N + 127) / 128);
+    region_fission_rate_kernel<<<rb, 128, 0, h->stream>>>(p, h->d.per_region_a);
+    pairwise_reduce_kernel<<<1, 256, 0, h->stream>>>(h->d.per_region_a, h->N, h->d.scalars, 0);
+    if (h->nranks > 1) {
+        int rc = allreduce_scalars(h, h->d.scalars, 1);   // solver.c:1190-1195
+        if (rc) return rc;
+    }
+    const long long cells = h->N * h->F * h->G;
+    scale_flux_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, h->stream>>>(p, h->d.scalars);
+    const long long n = 2 * h->T3 * h->G;
+    const long long n4 = n / 4;
+    scale_psi_kernel<<<148 * 8, 256, 0, h->stream>>>(reinterpret_cast<float4 *>(h->d.psi), n4, h->d.psi + 4 * n4,
+                                                    (int)(n - 4 * n4), h->d.scalars);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return MOC_OK;
+}
+
+extern "C" int moc_update_sources(moc_handle *h, float keff, float *res)
+{
+    if (!h) return MOC_EINVAL;
+    CUDA_TRY(cudaSetDevice(h->device));
+    const SourceParams p = source_params(h);
+    const float inverse_k = (float)(1.0 / (double)keff);   // solver.c:1241
+    const long long rows = h->N * h->F;
+    const int threads = std::min(128, (h->G + 31) / 32 * 32);
+    update_sources_kernel<<<(unsigned)rows, threads, sizeof(float) * 2 * (size_t)h->G, h->stream>>>(
+        p, inverse_k, h->d.per_fine);
+    region_fold_kernel<<<(unsigned)((h->N + 127) / 128), 128, 0, h->stream>>>(h->d.per_fine, h->N, h->F,
+                                                                             h->d.per_region_a);
+    pairwise_reduce_kernel<<<1, 256, 0, h->stream>>>(h->d.per_region_a, h->N, h->d.scalars, 1);
+    CUDA_TRY(cudaGetLastError());
+    float r = 0.f;
+    CUDA_TRY(cudaMemcpyAsync(&r, h->d.scalars + 1, sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    if (res) *res = r;
+    return MOC_OK;
+}
+
+extern "C" int moc_compute_keff(moc_handle *h, float *keff)
+{
+    if (!h) return MOC_EINVAL;
+    CUDA_TRY(cudaSetDevice(h->device));
+    const SourceParams p = source_params(h);
+    region_reaction_rates_kernel<<<(unsigned)((h->N + 127) / 128), 128, 0, h->stream>>>(p, h->d.per_region_a,
+                                                                                       h->d.per_region_b);
+    pairwise_reduce_kernel<<<1, 256, 0, h->stream>>>(h->d.per_region_a, h->N, h->d.scalars, 2);   // absorption
+    pairwise_reduce_kernel<<<1, 256, 0, h->stream>>>(h->d.per_region_b, h->N, h->d.scalars, 3);   // fission
+    CUDA_TRY(cudaMemcpyAsync(h->d.scalars + 4, h->d.leakage, sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
+    if (h->nranks > 1) {
+        int rc = allreduce_scalars(h, h->d.scalars + 2, 3);   // solver.c:1394-1418, one vector
+        if (rc) return rc;
+    }
+    float v[3];
+    CUDA_TRY(cudaMemcpyAsync(v, h->d.scalars + 2, sizeof(float) * 3, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    CUDA_TRY(cudaGetLastError());
+    if (keff) *keff = v[1] / (v[0] + v[2]);   // solver.c:1423,1425
+    return MOC_OK;
+}
+
+// ------------------------------------------------------------------ array access
+
+static int array_span(moc_handle *h, int which, void **ptr, size_t *bytes)
+{
+    const size_t T3 = (size_t)h->T3, G = (size_t)h->G, N = (size_t)h->N, F = (size_t)h->F;
+    switch (which) {
+    case MOC_ARR_FINE_SOURCE: *ptr = h->d.src; *bytes = sizeof(float) * N * F * G; return MOC_OK;
+    case MOC_ARR_FINE_FLUX: *ptr = h->d.src + N * F * G; *bytes = sizeof(float) * N * F * G; return MOC_OK;
+    case MOC_ARR_SIGT: *ptr = h->d.src + 2 * N * F * G; *bytes = sizeof(float) * N * G; return MOC_OK;
+    case MOC_ARR_PSI: *ptr = h->d.psi; *bytes = sizeof(float) * 2 * T3 * G; return MOC_OK;
+    case MOC_ARR_Z_HEIGHT: *ptr = h->d.z_height; *bytes = sizeof(float) * T3; return MOC_OK;
+    case MOC_ARR_P_WEIGHT: *ptr = h->d.p_weight; *bytes = sizeof(float) * T3; return MOC_OK;
+    case MOC_ARR_SEG_COUNT: *ptr = h->d.seg_count; *bytes = sizeof(uint32_t) * T3; return MOC_OK;
+    case MOC_ARR_QSR_DIGEST: *ptr = h->d.digest; *bytes = sizeof(unsigned long long) * 4; return MOC_OK;
+    }
+    moc_set_error("unknown array id %d", which);
+    return MOC_EINVAL;
+}
+
+extern "C" int moc_get_array(moc_handle *h, int which, void *dst, size_t bytes)
+{
+    if (!h || !dst) return MOC_EINVAL;
+    CUDA_TRY(cudaSetDevice(h->device));
+    void *p;
+    size_t n;
+    int rc = array_span(h, which, &p, &n);
+    if (rc) return rc;
+    if (bytes != n) {
+        moc_set_error("moc_get_array(%d): buffer is %zu bytes, array is %zu", which, bytes, n);
+        return MOC_EINVAL;
+    }
+    CUDA_TRY(cudaMemcpyAsync(dst, p, n, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return MOC_OK;
+}
+
+extern "C" int moc_set_array(moc_handle *h, int which, const void *src, size_t bytes)
+{
+    if (!h || !src) return MOC_EINVAL;
+    CUDA_TRY(cudaSetDevice(h->device));
+    void *p;
+    size_t n;
+    int rc = array_span(h, which, &p, &n);
+    if (rc) return rc;
+    if (bytes != n || which == MOC_ARR_SEG_COUNT || which == MOC_ARR_QSR_DIGEST) {
+        moc_set_error("moc_set_array(%d): read-only array or size mismatch (%zu vs %zu)", which, bytes, n);
+        return MOC_EINVAL;
+    }
+    CUDA_TRY(cudaMemcpyAsync(p, src, n, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return MOC_OK;
+}
+
+extern "C" float moc_get_leakage(moc_handle *h)
+{
+    if (!h) return 0.f;
+    cudaSetDevice(h->device);
+    float v = 0.f;
+    cudaMemcpyAsync(&v, h->d.leakage, sizeof(float), cudaMemcpyDeviceToHost, h->stream);
+    cudaStreamSynchronize(h->stream);
+    return v;
+}
+
+extern "C" int moc_synchronize(moc_handle *h)
+{
+    if (!h) return MOC_EINVAL;
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return MOC_OK;
+}
+
+// what: 1 = forward psi + z_height + fine_flux (what transport_sweep mutates)
+//       2 = everything mutable (psi both rows, z_height, whole source slab, leakage)
+static int download_into(moc_handle *h, const HostLayout &L, Params *P, int what)
+{
+    const size_t T3 = (size_t)h->T3, G = (size_t)h->G, N = (size_t)h->N, F = (size_t)h->F;
+    const int threads = 256;
+    patch_tracks_kernel<<<(unsigned)((T3 + threads - 1) / threads), threads, 0, h->stream>>>(
+        h->d.track_image, (long long)T3, h->d.z_height);
+    CUDA_TRY(cudaMemcpyAsync((void *)L.tracks, h->d.track_image, sizeof(TrackImage) * T3, cudaMemcpyDeviceToHost, h->stream));
+    if (what == 1) {
+        CUDA_TRY(cudaMemcpy2DAsync(L.psi, sizeof(float) * 2 * G, h->d.psi, sizeof(float) * 2 * G, sizeof(float) * G,
+                                   T3, cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(cudaMemcpyAsync(L.src + N * F * G, h->d.src + N * F * G, sizeof(float) * N * F * G,
+                                 cudaMemcpyDeviceToHost, h->stream));
+    } else {
+        CUDA_TRY(cudaMemcpyAsync(L.psi, h->d.psi, sizeof(float) * 2 * T3 * G, cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(cudaMemcpyAsync(L.src, h->d.src, sizeof(float) * (2 * F + 1) * N * G, cudaMemcpyDeviceToHost, h->stream));
+        if (P->leakage)
+            CUDA_TRY(cudaMemcpyAsync(P->leakage, h->d.leakage, sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    }
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    CUDA_TRY(cudaGetLastError());
+    return MOC_OK;
+}
+
+extern "C" int moc_download(moc_handle *h, Params *P)
+{
+    if (!h || !P) return MOC_EINVAL;
+    CUDA_TRY(cudaSetDevice(h->device));
+    HostLayout L;
+    int rc = inspect_layout(&h->I, P, h->source_stride, L);
+    if (rc) return rc;
+    return download_into(h, L, P, 2);
+}
+
+extern "C" int moc_upload(moc_handle *h, const Params *P)
+{
+    if (!h || !P) return MOC_EINVAL;
+    CUDA_TRY(cudaSetDevice(h->device));
+    HostLayout L;
+    int rc = inspect_layout(&h->I, P, h->source_stride, L);
+    if (rc) return rc;
+    if ((rc = upload_mutable(h, L, true))) return rc;
+    if (P->leakage) CUDA_TRY(cudaMemcpyAsync(h->d.leakage, P->leakage, sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return MOC_OK;
+}
+
+// ------------------------------------------------------------------ communication (NCCL, loaded lazily)
+
+// Minimal NCCL surface, resolved with dlopen so that single-GPU use has no NCCL dependency
+// and so that the library shares whichever libnccl the host process already loaded.
+typedef struct { char internal[128]; } nccl_unique_id;
+typedef int (*nccl_get_unique_id_t)(nccl_unique_id *);
+typedef int (*nccl_comm_init_rank_t)(void **, int, nccl_unique_id, int);
+typedef int (*nccl_comm_destroy_t)(void *);
+typedef int (*nccl_send_t)(const void *, size_t, int, int, void *, cudaStream_t);
+typedef int (*nccl_recv_t)(void *, size_t, int, int, void *, cudaStream_t);
+typedef int (*nccl_all_reduce_t)(const void *, void *, size_t, int, int, void *, cudaStream_t);
+typedef int (*nccl_group_t)(void);
+typedef const char *(*nccl_error_string_t)(int);
+
+static struct {
+    void *lib = nullptr;
+    nccl_get_unique_id_t get_unique_id = nullptr;
+    nccl_comm_init_rank_t comm_init_rank = nullptr;
+    nccl_comm_destroy_t comm_destroy = nullptr;
+    nccl_send_t send = nullptr;
+    nccl_recv_t recv = nullptr;
+    nccl_all_reduce_t all_reduce = nullptr;
+    nccl_group_t group_start = nullptr, group_end = nullptr;
+    nccl_error_string_t error_string = nullptr;
+} g_nccl;
+
+static int load_nccl()
+{
+    if (g_nccl.lib) return MOC_OK;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char *n : names) {
+        g_nccl.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (g_nccl.lib) break;
+    }
+    if (!g_nccl.lib) {
+        moc_set_error("cannot dlopen libnccl.so.2: %s", dlerror());
+        return MOC_ECOMM;
+    }
+#define MOC_SYM(field, name)                                                  \
+    g_nccl.field = (decltype(g_nccl.field))dlsym(g_nccl.lib, name);           \
+    if (!g_nccl.field) {                                                      \
+        moc_set_error("libnccl lacks %s", name);                              \
+        return MOC_ECOMM;                                                     \
+    }
+    MOC_SYM(get_unique_id, "ncclGetUniqueId")
+    MOC_SYM(comm_init_rank, "ncclCommInitRank")
+    MOC_SYM(comm_destroy, "ncclCommDestroy")
+    MOC_SYM(send, "ncclSend")
+    MOC_SYM(recv, "ncclRecv")
+    MOC_SYM(all_reduce, "ncclAllReduce")
+    MOC_SYM(group_start, "ncclGroupStart")
+    MOC_SYM(group_end, "ncclGroupEnd")
+    MOC_SYM(error_string, "ncclGetErrorString")
+#undef MOC_SYM
+    return MOC_OK;
+}
+
+#define NCCL_TRY(expr)                                                                         \
+    do {                                                                                       \
+        int res__ = (expr);                                                                    \
+        if (res__ != 0) {                                                                      \
+            moc_set_error("%s failed: %s", #expr, g_nccl.error_string ? g_nccl.error_string(res__) : "?"); \
+            return MOC_ECOMM;                                                                  \
+        }                                                                                      \
+    } while (0)
+
+extern "C" int moc_comm_get_unique_id(char id_out[128])
+{
+    int rc = load_nccl();
+    if (rc) return rc;
+    nccl_unique_id id;
+    NCCL_TRY(g_nccl.get_unique_id(&id));
+    memcpy(id_out, id.internal, 128);
+    return MOC_OK;
+}
+
+extern "C" int moc_comm_init(moc_handle *h, int nranks, int rank, const char id_in[128])
+{
+    if (!h || nranks < 1 || rank < 0 || rank >= nranks) {
+        moc_set_error("moc_comm_init: bad arguments");
+        return MOC_EINVAL;
+    }
+    int rc = load_nccl();
+    if (rc) return rc;
+    CUDA_TRY(cudaSetDevice(h->device));
+    nccl_unique_id id;
+    memcpy(id.internal, id_in, 128);
+    NCCL_TRY(g_nccl.comm_init_rank(&h->nccl_comm, nranks, id, rank));
+    h->nranks = nranks;
+    h->rank = rank;
+    return MOC_OK;
+}
+
+static int allreduce_scalars(moc_handle *h, float *dev, int count)
+{
+    if (!h->nccl_comm) {
+        moc_set_error("multi-rank reduction without moc_comm_init");
+        return MOC_ECOMM;
+    }
+    NCCL_TRY(g_nccl.all_reduce(dev, dev, (size_t)count, /*ncclFloat*/ 7, /*ncclSum*/ 0, h->nccl_comm, h->stream));
+    return MOC_OK;
+}
+
+// comms.c:12-28,75-83: tracks per face, in whole messages of 10000 tracks
+static void exchange_plan(const Input &I, long num_messages[6])
+{
+    const int tracks_per_msg = 10000;
+    const float hgt = I.domain_height;
+    const float x = I.assembly_width;
+    long per_axial = I.ntracks * x / (2 * x + 4 * hgt);
+    long per_radial = I.ntracks * hgt / (2 * x + 4 * hgt);
+    const long remaining = I.ntracks - 2 * per_axial - 4 * per_radial;
+    long add_radial = remaining * (4 * hgt / (2 * x + 4 * hgt));
+    add_radial = 4 * (add_radial / 4);
+    per_radial += add_radial / 4;
+    const long add_axial = remaining - add_radial;
+    per_axial += add_axial / 2;
+    for (int d = 0; d < 4; d++) num_messages[d] = per_radial / tracks_per_msg;
+    for (int d = 4; d < 6; d++) num_messages[d] = per_axial / tracks_per_msg;
+}
+
+// fast_transfer_boundary_fluxes (comms.c:5-196) on the device.  Chunks sit at the head of
+// the psi slab in (round, direction) order.  Border faces: the chunk's pairwise sum goes to
+// the leakage, zeros come back.  Interior faces: ncclSend of the chunk to *_dest, ncclRecv
+// from *_src into a staging buffer, copied back over the same offsets after the group.
+extern "C" int moc_exchange(moc_handle *h, const CommGrid *grid)
+{
+    if (!h || !grid) return MOC_EINVAL;
+    CUDA_TRY(cudaSetDevice(h->device));
+    long nmsg[6];
+    exchange_plan(h->I, nmsg);
+    const long long chunk = (long long)h->G * 10000;
+    long rounds = 0, total_chunks = 0;
+    for (int d = 0; d < 6; d++) {
+        rounds = std::max(rounds, nmsg[d]);
+        total_chunks += nmsg[d];
+    }
+    if (total_chunks * chunk > 2 * h->T3 * h->G) {
+        moc_set_error("exchange plan exceeds the flux slab");
+        return MOC_EINVAL;
+    }
+    if (total_chunks == 0) return MOC_OK;
+    const int dest[6] = {grid->x_pos_dest, grid->x_neg_dest, grid->y_pos_dest,
+                         grid->y_neg_dest, grid->z_pos_dest, grid->z_neg_dest};
+    const int from[6] = {grid->x_pos_src, grid->x_neg_src, grid->y_pos_src,
+                         grid->y_neg_src, grid->z_pos_src, grid->z_neg_src};
+    bool any_peer = false;
+    for (int d = 0; d < 6; d++) any_peer = any_peer || dest[d] != -1 || from[d] != -1;
+    if (any_peer && !h->nccl_comm) {
+        moc_set_error("moc_exchange: neighbours present but moc_comm_init was not called");
+        return MOC_ECOMM;
+    }
+    if (any_peer && !h->recv_stage) {
+        CUDA_TRY(cudaMalloc((void **)&h->recv_stage, sizeof(float) * (size_t)total_chunks * chunk));
+    }
+    // 1) leakage of border faces, in the reference's (round, direction) accumulation order
+    {
+        long long at = 0;
+        for (long i = 0; i < rounds; i++)
+            for (int d = 0; d < 6; d++) {
+                if (i >= nmsg[d]) continue;
+                if (dest[d] == -1)
+                    chunk_leakage_kernel<<<1, 256, 0, h->stream>>>(h->d.psi + at, chunk, h->d.leakage);
+                at += chunk;
+            }
+    }
+    // 2) all sends and receives of all rounds in one NCCL group (tag = direction is implied by
+    //    the per-peer FIFO order, which is the (round, direction) order on both sides)
+    if (any_peer) {
+        NCCL_TRY(g_nccl.group_start());
+        long long at = 0;
+        for (long i = 0; i < rounds; i++)
+            for (int d = 0; d < 6; d++) {
+                if (i >= nmsg[d]) continue;
+                if (dest[d] != -1)
+                    NCCL_TRY(g_nccl.send(h->d.psi + at, (size_t)chunk, 7, dest[d], h->nccl_comm, h->stream));
+                if (from[d] != -1)
+                    NCCL_TRY(g_nccl.recv(h->recv_stage + at, (size_t)chunk, 7, from[d], h->nccl_comm, h->stream));
+                at += chunk;
+            }
+        NCCL_TRY(g_nccl.group_end());
+    }
+    // 3) received chunks (or zeros) replace the sent ones
+    {
+        long long at = 0;
+        for (long i = 0; i < rounds; i++)
+            for (int d = 0; d < 6; d++) {
+                if (i >= nmsg[d]) continue;
+                if (from[d] == -1)
+                    CUDA_TRY(cudaMemsetAsync(h->d.psi + at, 0, sizeof(float) * (size_t)chunk, h->stream));
+                else
+                    CUDA_TRY(cudaMemcpyAsync(h->d.psi + at, h->recv_stage + at, sizeof(float) * (size_t)chunk,
+                                             cudaMemcpyDeviceToDevice, h->stream));
+                at += chunk;
+            }
+    }
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    CUDA_TRY(cudaGetLastError());
+    return MOC_OK;
+}
+
+// init.c:162-225 generalised from the hard-coded {2,2,1} to cx*cy*cz (MPI_Cart_create row-major
+// ranks, MPI_Cart_shift neighbours, -1 at the non-periodic border)
+extern "C" int moc_make_grid(int cx, int cy, int cz, int rank, CommGrid *g)
+{
+    if (!g || cx < 1 || cy < 1 || cz < 1 || rank < 0 || rank >= cx * cy * cz) {
+        moc_set_error("moc_make_grid: bad grid %dx%dx%d rank %d", cx, cy, cz, rank);
+        return MOC_EINVAL;
+    }
+    const int dims[3] = {cx, cy, cz};
+    const int at[3] = {rank / (cy * cz), (rank / cz) % cy, rank % cz};
+    auto rank_of = [&](int a, int delta) {
+        int c[3] = {at[0], at[1], at[2]};
+        c[a] += delta;
+        if (c[a] < 0 || c[a] >= dims[a]) return -1;
+        return (c[0] * cy + c[1]) * cz + c[2];
+    };
+    int *pos_src[3] = {&g->x_pos_src, &g->y_pos_src, &g->z_pos_src};
+    int *pos_dest[3] = {&g->x_pos_dest, &g->y_pos_dest, &g->z_pos_dest};
+    int *neg_src[3] = {&g->x_neg_src, &g->y_neg_src, &g->z_neg_src};
+    int *neg_dest[3] = {&g->x_neg_dest, &g->y_neg_dest, &g->z_neg_dest};
+    for (int a = 0; a < 3; a++) {
+        *pos_src[a] = rank_of(a, -1);   // MPI_Cart_shift(+1): receive from below, send up
+        *pos_dest[a] = rank_of(a, +1);
+        *neg_src[a] = rank_of(a, +1);   // MPI_Cart_shift(-1): receive from above, send down
+        *neg_dest[a] = rank_of(a, -1);
+    }
+    return MOC_OK;
+}
+
+// ------------------------------------------------------------------ drop-in entry points (PART B1)
+
+struct Mirror {
+    moc_handle *h = nullptr;
+    bool dirty_sweep = false;   // device holds newer psi/z/flux than the host
+    bool dirty_all = false;     // device holds newer everything
+};
+static std::mutex g_mirror_mutex;
+static std::unordered_map<const void *, Mirror> g_mirrors;   // keyed by Params.tracks
+static int g_resident = 0;
+static unsigned long long g_dropin_seed = 1, g_dropin_rand_base = 0;
+static int g_dropin_exp_mode = 0, g_dropin_source_stride = 48;
+
+extern "C" void moc_set_resident(int on) { g_resident = on ? 1 : 0; }
+
+// options applied to mirrors created by the drop-in entry points
+extern "C" void moc_dropin_configure(unsigned long long seed, unsigned long long rand_base, int exp_mode,
+                                     int source_stride)
+{
+    g_dropin_seed = seed;
+    g_dropin_rand_base = rand_base;
+    g_dropin_exp_mode = exp_mode;
+    g_dropin_source_stride = source_stride;
+}
+
+[[noreturn]] static void die(const char *where)
+{
+    // the reference has no error returns on this path: it prints and exits (solver.c:506-511)
+    fprintf(stderr, "libmoc_b200: %s: %s\n", where, moc_last_error());
+    exit(1);
+}
+
+// Find (or build) the device mirror of a host Params.  Non-resident mode re-uploads the
+// mutable state on every call (host is authoritative); resident mode uploads once.
+static Mirror &mirror_for(const Params *P, const Input *I, HostLayout &L, bool need_backward_psi,
+                          const char *where)
+{
+    std::lock_guard<std::mutex> lock(g_mirror_mutex);
+    Mirror &m = g_mirrors[(const void *)P->tracks];
+    bool created = false;
+    if (!m.h) {
+        int device = 0;
+        cudaGetDevice(&device);
+        if (create_common(I, P, device, g_dropin_source_stride, &m.h, L)) die(where);
+        m.h->seed = g_dropin_seed;
+        m.h->rand_base = g_dropin_rand_base;
+        m.h->exp_mode = g_dropin_exp_mode;
+        created = true;
+    } else if (inspect_layout(I, P, m.h->source_stride, L)) {
+        die(where);
+    }
+    if (created || !g_resident) {
+        if (upload_mutable(m.h, L, created || need_backward_psi)) die(where);
+        if (P->leakage)
+            cudaMemcpyAsync(m.h->d.leakage, P->leakage, sizeof(float), cudaMemcpyHostToDevice, m.h->stream);
+    }
+    return m;
+}
+
+extern "C" void transport_sweep(Params *params, Input *I)
+{
+    HostLayout L;
+    Mirror &m = mirror_for(params, I, L, false, "transport_sweep");
+    long segs = 0;
+    if (moc_sweep(m.h, &segs)) die("transport_sweep");
+    I->segments_processed = segs;
+    if (g_resident) {
+        m.dirty_sweep = true;
+    } else if (download_into(m.h, L, params, 1)) {
+        die("transport_sweep");
+    }
+}
+
+extern "C" void renormalize_flux(Params params, Input I, CommGrid grid)
+{
+    (void)grid;
+    HostLayout L;
+    Mirror &m = mirror_for(&params, &I, L, true, "renormalize_flux");
+    if (moc_renormalize(m.h)) die("renormalize_flux");
+    if (g_resident) m.dirty_all = true;
+    else if (download_into(m.h, L, &params, 2)) die("renormalize_flux");
+}
+
+extern "C" float update_sources(Params params, Input I, float keff)
+{
+    HostLayout L;
+    Mirror &m = mirror_for(&params, &I, L, false, "update_sources");
+    float res = 0.f;
+    if (moc_update_sources(m.h, keff, &res)) die("update_sources");
+    if (g_resident) m.dirty_all = true;
+    else {
+        // only fine_source changes
+        const size_t n = sizeof(float) * (size_t)m.h->N * m.h->F * m.h->G;
+        if (cudaMemcpyAsync(L.src, m.h->d.src, n, cudaMemcpyDeviceToHost, m.h->stream) != cudaSuccess ||
+            cudaStreamSynchronize(m.h->stream) != cudaSuccess) {
+            moc_set_error("download of fine_source failed");
+            die("update_sources");
+        }
+    }
+    return res;
+}
+
+extern "C" float compute_keff(Params params, Input I, CommGrid grid)
+{
+    (void)grid;
+    HostLayout L;
+    Mirror &m = mirror_for(&params, &I, L, false, "compute_keff");
+    float k = 0.f;
+    if (moc_compute_keff(m.h, &k)) die("compute_keff");
+    return k;
+}
+
+extern "C" void fast_transfer_boundary_fluxes(Params params, Input I, CommGrid grid)
+{
+    HostLayout L;
+    Mirror &m = mirror_for(&params, &I, L, true, "fast_transfer_boundary_fluxes");
+    if (moc_exchange(m.h, &grid)) die("fast_transfer_boundary_fluxes");
+    if (g_resident) m.dirty_all = true;
+    else if (download_into(m.h, L, &params, 2)) die("fast_transfer_boundary_fluxes");
+}
+
+extern "C" int moc_sync_to_host(Params *params)
+{
+    if (!params) return MOC_EINVAL;
+    std::lock_guard<std::mutex> lock(g_mirror_mutex);
+    auto it = g_mirrors.find((const void *)params->tracks);
+    if (it == g_mirrors.end() || !it->second.h) {
+        moc_set_error("moc_sync_to_host: no device mirror for this Params");
+        return MOC_EINVAL;
+    }
+    Mirror &m = it->second;
+    HostLayout L;
+    int rc = inspect_layout(&m.h->I, params, m.h->source_stride, L);
+    if (rc) return rc;
+    rc = download_into(m.h, L, params, 2);
+    if (!rc) m.dirty_sweep = m.dirty_all = false;
+    return rc;
+}
+
+extern "C" int moc_release(Params *params)
+{
+    if (!params) return MOC_EINVAL;
+    std::lock_guard<std::mutex> lock(g_mirror_mutex);
+    auto it = g_mirrors.find((const void *)params->tracks);
+    if (it == g_mirrors.end()) return MOC_OK;
+    moc_destroy(it->second.h);
+    g_mirrors.erase(it);
+    return MOC_OK;
+}
+
+// the handle behind a Params used through the drop-in names (for timing queries)
+extern "C" moc_handle *moc_handle_of(Params *params)
+{
+    std::lock_guard<std::mutex> lock(g_mirror_mutex);
+    auto it = g_mirrors.find((const void *)params->tracks);
+    return it == g_mirrors.end() ? nullptr : it->second.h;
+}

@@ -1,0 +1,508 @@
+/* moc_host.c -- host side of libmoc_b200.so: configuration, command line and
+ * synthetic problem construction (PART B3 of include/moc_b200.h).
+ *
+ * Mirrors the behaviour of the reference's init.c / io.c / tracks.c / source.c
+ * (cited per function, paths relative to /root/reference/src) but is organised
+ * around the counter-based random stream of include/moc_rng.h: every array is
+ * filled from a closed-form stream position (moc_draw_layout), so the
+ * construction can be evaluated in any order while consuming draws in exactly
+ * the order the reference's serial code does.
+ *
+ * The big slabs come from moc_host_alloc() (pinned when a CUDA device is
+ * present, so the drop-in path can DMA straight out of them).
+ */
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "moc_b200.h"
+#include "moc_internal.h"
+#include "moc_rng.h"
+
+/* ------------------------------------------------------------------ errors */
+static __thread char g_error[512];
+
+void moc_set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof g_error, fmt, ap);
+    va_end(ap);
+}
+
+const char *moc_last_error(void) { return g_error; }
+
+/* ------------------------------------------------------------------ defaults */
+
+/* init.c:33-74 -- the "default strawman" problem (~13 GB) */
+Input moc_set_default_input(void)
+{
+    Input in;
+    memset(&in, 0, sizeof in);
+    in.x_assemblies = 17;
+    in.y_assemblies = 17;
+    in.cai = 27;
+    in.fai = 5;
+    in.axial_exp = 2;
+    in.radial_ray_sep = 0.05;
+    in.axial_z_sep = 0.25;
+    in.n_azimuthal = 64;
+    in.n_polar_angles = 10;
+    in.n_egroups = 104;
+    in.decompose = true;
+    in.decomp_assemblies_ax = 20;
+    in.segments_per_track = 120;
+    in.assembly_width = 21.42;
+    in.height = 400.0;
+    in.precision = 0.01;
+    in.mype = 0;
+    in.n_2D_source_regions_per_assembly = 5000;
+    in.nthreads = 1;
+    in.load_tracks = false;
+    in.track_file = NULL;
+    return in;
+}
+
+/* init.c:77-103 -- the "-s" problem (~1 GB) */
+void moc_set_small_input(Input *in)
+{
+    in->x_assemblies = 15;
+    in->y_assemblies = 15;
+    in->cai = 5;
+    in->fai = 3;
+    in->axial_exp = 2;
+    in->radial_ray_sep = 0.5;
+    in->axial_z_sep = 0.2;
+    in->n_azimuthal = 5;
+    in->n_polar_angles = 5;
+    in->n_egroups = 104;
+    in->decompose = false;
+    in->decomp_assemblies_ax = 1;
+    in->segments_per_track = 120;
+    in->assembly_width = 1.26 * 17;
+    in->height = 400.0;
+    in->precision = 0.01;
+    in->n_2D_source_regions_per_assembly = 3000;
+}
+
+/* init.c:4-30 */
+void moc_calculate_derived_inputs(Input *in)
+{
+    in->n_azimuthal /= 2;   /* forward/backward tracking shares a 2D track */
+    in->ntracks_2D = in->n_azimuthal * (in->assembly_width * sqrt(2) / in->radial_ray_sep);
+    in->ntracks_2D = 2 * (in->ntracks_2D / 2);
+    in->z_stacked = (int)(in->height / (in->axial_z_sep * in->decomp_assemblies_ax));
+    in->ntracks = in->ntracks_2D * in->n_polar_angles * in->z_stacked;
+    in->domain_height = in->height / in->decomp_assemblies_ax;
+    in->n_source_regions_per_node =
+        in->n_2D_source_regions_per_assembly * in->cai / in->decomp_assemblies_ax;
+}
+
+/* io.c:198-270 -- 18 values, each the leading token of a line; the rest of the line
+ * is commentary.  Integers are read like "%d"/"%ld", reals like "%f". */
+int moc_read_input_file(Input *in, const char *fname)
+{
+    enum { KI, KL, KF, KB };
+    struct { int kind; void *dst; } slot[18] = {
+        { KI, &in->x_assemblies }, { KI, &in->y_assemblies }, { KI, &in->cai },
+        { KI, &in->fai }, { KI, &in->axial_exp }, { KF, &in->radial_ray_sep },
+        { KF, &in->axial_z_sep }, { KI, &in->n_azimuthal }, { KI, &in->n_polar_angles },
+        { KI, &in->n_egroups }, { KB, &in->decompose }, { KI, &in->decomp_assemblies_ax },
+        { KL, &in->segments_per_track }, { KF, &in->assembly_width }, { KF, &in->height },
+        { KF, &in->precision }, { KL, &in->n_2D_source_regions_per_assembly },
+        { KI, &in->papi_event_set } };
+
+    FILE *fp = fopen(fname, "r");
+    if (!fp) {
+        moc_set_error("cannot open input file '%s'", fname);
+        return MOC_EINVAL;
+    }
+    char line[512];
+    int got = 0;
+    while (got < 18 && fgets(line, sizeof line, fp)) {
+        char *p = line, *end = NULL;
+        while (*p == ' ' || *p == '\t') p++;
+        if (*p == '\n' || *p == '\r' || *p == '\0') continue;
+        switch (slot[got].kind) {
+        case KI: *(int *)slot[got].dst = (int)strtol(p, &end, 10); break;
+        case KL: *(long *)slot[got].dst = strtol(p, &end, 10); break;
+        case KF: *(float *)slot[got].dst = strtof(p, &end); break;
+        case KB: *(bool *)slot[got].dst = strtol(p, &end, 10) != 0; break;
+        }
+        if (end == p) {
+            fclose(fp);
+            moc_set_error("input file '%s': line for value %d does not start with a number",
+                          fname, got + 1);
+            return MOC_EINVAL;
+        }
+        got++;
+    }
+    fclose(fp);
+    if (got < 18) {
+        moc_set_error("input file '%s': expected 18 values, found %d", fname, got);
+        return MOC_EINVAL;
+    }
+    return MOC_OK;
+}
+
+/* io.c:115-181.  Options are applied in command-line order, as in the reference
+ * (so "-i f -s" ends with the small set, "-s -i f" with the file's). */
+int moc_read_CLI(int argc, char *argv[], Input *in)
+{
+    in->nthreads = 1;
+    for (int a = 1; a < argc; a++) {
+        const char *opt = argv[a];
+        int has_value = (a + 1 < argc);
+        if (strcmp(opt, "-t") == 0) {
+            if (!has_value) goto usage;
+            in->nthreads = atoi(argv[++a]);   /* accepted for compatibility; the GPU path ignores it */
+        } else if (strcmp(opt, "-i") == 0) {
+            if (!has_value) goto usage;
+            int rc = moc_read_input_file(in, argv[++a]);
+            if (rc) return rc;
+        } else if (strcmp(opt, "-s") == 0) {
+            moc_set_small_input(in);
+        } else if (strcmp(opt, "-d") == 0) {
+            if (!has_value) goto usage;
+            in->track_file = argv[++a];
+            in->load_tracks = true;
+        } else if (strcmp(opt, "-p") == 0) {
+            if (!has_value) goto usage;
+            ++a;                              /* PAPI event name: CPU counters do not apply */
+        } else {
+            goto usage;
+        }
+    }
+    if (in->nthreads < 1) goto usage;
+    return MOC_OK;
+usage:
+    moc_set_error("usage: SimpleMOC-b200 [-t <threads>] [-i <input file>] [-s] [-d <OpenMOC track file>]");
+    return MOC_EINVAL;
+}
+
+/* utils.c:97-143 -- the reference's own footprint estimate, same terms */
+size_t moc_est_mem_usage(const Input *in)
+{
+    const size_t T2 = (size_t)in->ntracks_2D, T3 = (size_t)in->ntracks;
+    const size_t P = (size_t)in->n_polar_angles, G = (size_t)in->n_egroups;
+    const size_t N = (size_t)in->n_source_regions_per_node, F = (size_t)in->fai;
+    const size_t X = N / 8;
+    const size_t Z = (size_t)(int)(in->height / (in->axial_z_sep * in->decomp_assemblies_ax));
+    const size_t nthr = (size_t)in->nthreads, Zs = (size_t)in->z_stacked;
+    const size_t spt = (size_t)in->segments_per_track;
+    size_t b = 0;
+    b += T2 * sizeof(Track2D) + spt * T2 * sizeof(Segment);
+    b += T2 * sizeof(Track **) + T2 * P * sizeof(Track *) + T3 * sizeof(Track);
+    b += T2 * P * Z * G * sizeof(float) * 2;                       /* angular flux */
+    b += N * sizeof(Source);
+    b += 3 * X * sizeof(float **) + X * G * G * sizeof(float);
+    b += X * G * sizeof(float *) + X * G * 3 * sizeof(float);
+    b += 2 * (N * sizeof(float **) + N * F * sizeof(float *));
+    b += N * F * G * sizeof(float);
+    /* per-thread two-way tracking scratch the reference still counts */
+    b += nthr * Zs * (sizeof(double *) + sizeof(Source **) + 2 * sizeof(int));
+    b += nthr * Zs * 2 * spt * (sizeof(double) + sizeof(Source *));
+    return b;
+}
+
+/* utils.c:147-155 */
+double moc_time_per_intersection(const Input *in, double seconds)
+{
+    return seconds / (double)in->segments_processed * 1.0e9 / (double)in->n_egroups;
+}
+
+/* ------------------------------------------------------------------ construction */
+
+/* utils.c:11-26 with explicit stream positions */
+static float normal_draw(uint64_t seed, uint64_t at, float mean, float sigma)
+{
+    float u_radius = moc_urand(seed, at);
+    float u_angle = moc_urand(seed, at + 1);
+    float x = sqrt(-2 * log(u_radius)) * cos(2 * M_PI * u_angle);
+    return x * sigma + mean;
+}
+
+/* utils.c:48-78 */
+static int make_exp_table(Table *tab, float precision, float maxVal)
+{
+    int cells = (int)(maxVal * sqrt(1.0 / (8.0 * precision * 0.01)));
+    float dx = maxVal / (float)cells;
+    float *v = (float *)malloc(sizeof(float) * 2 * (size_t)cells);
+    if (!v) return MOC_ENOMEM;
+    for (int n = 0; n < cells; n++) {
+        float e = exp(-n * dx);
+        v[2 * n] = -e;                       /* slope, as the reference stores it */
+        v[2 * n + 1] = 1 + (n * dx - 1) * e; /* intercept */
+    }
+    tab->values = v;
+    tab->dx = dx;
+    tab->maxVal = maxVal - dx;
+    tab->N = cells;
+    return MOC_OK;
+}
+
+/* init.c:106-159 = tracks.c:4-58 + tracks.c:75-168 + source.c:4-214 + utils.c:48-78 */
+int moc_build_tracks(const Input *in, uint64_t seed, Params *out, uint64_t *rand_calls)
+{
+    if (in->load_tracks) {
+        moc_set_error("OpenMOC track files (-d, reference tracks.c:170-323) are out of scope: "
+                      "no sample file ships with the reference");
+        return MOC_EINVAL;
+    }
+    if (in->ntracks_2D <= 0 || in->z_stacked <= 0 || in->n_polar_angles <= 0 ||
+        in->n_egroups <= 0 || in->fai <= 0 || in->n_source_regions_per_node < 8) {
+        moc_set_error("degenerate problem: T2=%ld Z=%d P=%d G=%d fai=%d N=%ld (need N >= 8)",
+                      in->ntracks_2D, in->z_stacked, in->n_polar_angles, in->n_egroups,
+                      in->fai, in->n_source_regions_per_node);
+        return MOC_EINVAL;
+    }
+    const long T2 = in->ntracks_2D, T3 = in->ntracks, N = in->n_source_regions_per_node;
+    const long X = N / 8;                                   /* source.c:12 */
+    const int P = in->n_polar_angles, Z = in->z_stacked, G = in->n_egroups, F = in->fai;
+    memset(out, 0, sizeof *out);
+
+    moc_draw_layout at;
+    at.az_weight = 0;
+    at.n_segments = at.az_weight + (uint64_t)T2;
+    at.seg_length = at.n_segments + 2 * (uint64_t)T2;
+
+    /* ---- 2D tracks ---- */
+    Track2D *t2 = (Track2D *)calloc((size_t)T2, sizeof(Track2D));
+    if (!t2) return MOC_ENOMEM;
+    long total_segments = 0;
+    for (long i = 0; i < T2; i++) {
+        t2[i].az_weight = moc_urand(seed, at.az_weight + (uint64_t)i);
+        t2[i].n_segments = normal_draw(seed, at.n_segments + 2 * (uint64_t)i,
+                                       in->segments_per_track, sqrt(in->segments_per_track));
+        if (t2[i].n_segments < 0) t2[i].n_segments = 0;   /* cannot index a negative count */
+        total_segments += t2[i].n_segments;
+    }
+    Segment *segs = (Segment *)calloc((size_t)(total_segments > 0 ? total_segments : 1), sizeof(Segment));
+    if (!segs) return MOC_ENOMEM;
+    {
+        long first = 0;
+        for (long i = 0; i < T2; i++) {
+            t2[i].segments = segs + first;
+            for (long n = 0; n < t2[i].n_segments; n++)
+                segs[first + n].length = moc_urand(seed, at.seg_length + (uint64_t)(first + n))
+                                         * in->assembly_width / t2[i].n_segments;
+            first += t2[i].n_segments;
+        }
+    }
+    out->tracks_2D = t2;
+    at.p_weight = at.seg_length + (uint64_t)total_segments;
+
+    /* ---- 3D tracks: [i][j][k] views over one Track array and one flux slab ---- */
+    Track ***by_i = (Track ***)malloc(sizeof(Track **) * (size_t)T2);
+    Track **by_ij = (Track **)malloc(sizeof(Track *) * (size_t)T2 * P);
+    Track *trk = (Track *)moc_host_alloc(sizeof(Track) * (size_t)T3);
+    float *flux = (float *)moc_host_alloc(sizeof(float) * 2 * (size_t)T3 * G);   /* zero-filled */
+    if (!by_i || !by_ij || !trk || !flux) return MOC_ENOMEM;
+    for (long i = 0; i < T2; i++) {
+        by_i[i] = by_ij + i * P;
+        for (int j = 0; j < P; j++) by_i[i][j] = trk + (i * P + j) * Z;
+    }
+    for (long t = 0; t < T3; t++) {
+        const int k = (int)(t % Z), j = (int)((t / Z) % P);
+        /* upward rays start at the bottom of their slot, downward ones at the top */
+        trk[t].z_height = (j < P / 2) ? in->axial_z_sep * k : in->axial_z_sep * (k + 1);
+        trk[t].p_weight = moc_urand(seed, at.p_weight + (uint64_t)t);
+        trk[t].f_psi = flux + 2 * t * G;
+        trk[t].b_psi = flux + (2 * t + 1) * G;
+    }
+    out->tracks = by_i;
+
+    float *polar = (float *)malloc(sizeof(float) * (size_t)P);
+    for (int j = 0; j < P; j++) polar[j] = M_PI * (j + 0.5) / P;       /* tracks.c:159-168 */
+    out->polar_angles = polar;
+
+    /* ---- sources ---- */
+    at.scatter = at.p_weight + (uint64_t)T3;
+    at.xs = at.scatter + (uint64_t)X * G * G;
+    at.fine_source = at.xs + (uint64_t)X * G * 3;
+    at.sigT = at.fine_source + (uint64_t)N * F * G;
+    at.regions = at.sigT + (uint64_t)N * G;
+    at.end = at.regions + 2 * (uint64_t)N - 1;
+
+    float *scat = (float *)moc_host_alloc(sizeof(float) * (size_t)X * G * G);
+    float *xs = (float *)moc_host_alloc(sizeof(float) * (size_t)X * G * 3);
+    /* one slab: fine_source[N][fai][G] | fine_flux[N][fai][G] | sigT[N][G]  (source.c:121-152) */
+    float *slab = (float *)moc_host_alloc(sizeof(float) * (size_t)(2 * F + 1) * N * G);
+    float **scat_rows = (float **)malloc(sizeof(float *) * (size_t)X * G);
+    float **xs_rows = (float **)malloc(sizeof(float *) * (size_t)X * G);
+    float **src_rows = (float **)malloc(sizeof(float *) * (size_t)N * F);
+    float **flux_rows = (float **)malloc(sizeof(float *) * (size_t)N * F);
+    Source *regions = (Source *)calloc((size_t)N, sizeof(Source));
+    if (!scat || !xs || !slab || !scat_rows || !xs_rows || !src_rows || !flux_rows || !regions)
+        return MOC_ENOMEM;
+
+    for (long e = 0; e < X * G * G; e++) scat[e] = moc_urand(seed, at.scatter + (uint64_t)e);
+    for (long e = 0; e < X * G * 3; e++) xs[e] = moc_urand(seed, at.xs + (uint64_t)e);
+    for (long e = 0; e < N * F * G; e++) slab[e] = moc_urand(seed, at.fine_source + (uint64_t)e);
+    float *sigT = slab + 2 * N * F * G;
+    for (long e = 0; e < N * G; e++) sigT[e] = moc_urand(seed, at.sigT + (uint64_t)e);
+    for (long r = 0; r < X * G; r++) {
+        scat_rows[r] = scat + r * G;
+        xs_rows[r] = xs + r * 3;
+    }
+    for (long r = 0; r < N * F; r++) {
+        src_rows[r] = slab + r * G;
+        flux_rows[r] = slab + (N * F + r) * G;
+    }
+    for (long i = 0; i < N; i++) {
+        /* region 0 takes material 0 without a draw; region i>0 draws (index, volume) */
+        long material = 0;
+        uint64_t vol_at = at.regions;
+        if (i > 0) {
+            material = (long)moc_rand31(seed, at.regions + 2 * (uint64_t)i - 1) % X;
+            vol_at = at.regions + 2 * (uint64_t)i;
+        }
+        regions[i].scattering_matrix = scat_rows + material * G;
+        regions[i].XS = xs_rows + material * G;
+        regions[i].fine_flux = flux_rows + i * F;
+        regions[i].fine_source = src_rows + i * F;
+        regions[i].sigT = sigT + i * G;
+        regions[i].vol = moc_urand(seed, vol_at);
+    }
+    out->sources = regions;
+
+    out->leakage = (float *)calloc(1, sizeof(float));
+    int rc = make_exp_table(&out->expTable, in->precision, 10.0);
+    if (rc) return rc;
+    if (rand_calls) *rand_calls = at.end;
+    return MOC_OK;
+}
+
+void moc_free_tracks(const Input *in, Params *p)
+{
+    (void)in;
+    if (!p) return;
+    if (p->tracks_2D) {
+        free(p->tracks_2D[0].segments);
+        free(p->tracks_2D);
+    }
+    if (p->tracks) {
+        Track *trk = p->tracks[0][0];
+        moc_host_free(trk[0].f_psi);
+        moc_host_free(trk);
+        free(p->tracks[0]);
+        free(p->tracks);
+    }
+    if (p->sources) {
+        Source *s0 = &p->sources[0];
+        moc_host_free(s0->scattering_matrix[0]);
+        free(s0->scattering_matrix);
+        moc_host_free(s0->XS[0]);
+        free(s0->XS);
+        moc_host_free(s0->fine_source[0]);
+        free(s0->fine_source);
+        free(s0->fine_flux);
+        free(p->sources);
+    }
+    free(p->polar_angles);
+    free(p->leakage);
+    free(p->expTable.values);
+    memset(p, 0, sizeof *p);
+}
+
+/* ------------------------------------------------------------------ flat views */
+
+static long params_copy(const Input *in, const Params *p, int which, void *dst, const void *src,
+                        size_t bytes)
+{
+    const long T2 = in->ntracks_2D, T3 = in->ntracks, N = in->n_source_regions_per_node, X = N / 8;
+    const int P = in->n_polar_angles, G = in->n_egroups, F = in->fai;
+    const Source *s0 = &p->sources[0];
+    Track *trk = p->tracks[0][0];
+    void *flat = NULL;      /* contiguous arrays: plain memcpy */
+    size_t n = 0;
+    switch (which) {
+    case MOC_ARR_FINE_SOURCE: flat = s0->fine_source[0]; n = sizeof(float) * N * F * G; break;
+    case MOC_ARR_FINE_FLUX: flat = s0->fine_flux[0]; n = sizeof(float) * N * F * G; break;
+    case MOC_ARR_SIGT: flat = s0->sigT; n = sizeof(float) * N * G; break;
+    case MOC_ARR_PSI: flat = trk[0].f_psi; n = sizeof(float) * 2 * T3 * G; break;
+    case MOC_HOST_XS: flat = s0->XS[0]; n = sizeof(float) * X * G * 3; break;
+    case MOC_HOST_SCATTER: flat = s0->scattering_matrix[0]; n = sizeof(float) * X * G * G; break;
+    case MOC_HOST_POLAR: flat = p->polar_angles; n = sizeof(float) * P; break;
+    case MOC_HOST_TABLE: flat = p->expTable.values; n = sizeof(float) * 2 * p->expTable.N; break;
+    case MOC_ARR_Z_HEIGHT:
+    case MOC_ARR_P_WEIGHT: n = sizeof(float) * T3; break;
+    case MOC_HOST_AZ_WEIGHT: n = sizeof(float) * T2; break;
+    case MOC_HOST_N_SEGMENTS: n = sizeof(long) * T2; break;
+    case MOC_HOST_SEG_LENGTHS: {
+        long tot = 0;
+        for (long i = 0; i < T2; i++) tot += p->tracks_2D[i].n_segments;
+        n = sizeof(float) * tot;
+        break;
+    }
+    case MOC_HOST_XS_INDEX: n = sizeof(int) * N; break;
+    case MOC_HOST_VOL: n = sizeof(float) * N; break;
+    default:
+        moc_set_error("moc_params_get/set: unknown array id %d", which);
+        return MOC_EINVAL;
+    }
+    if ((!dst && !src) || bytes != n) return (long)n;
+    if (flat) {
+        if (dst) memcpy(dst, flat, n);
+        else memcpy(flat, src, n);
+        return (long)n;
+    }
+    /* strided members of the AoS structures */
+    switch (which) {
+    case MOC_ARR_Z_HEIGHT:
+        for (long t = 0; t < T3; t++) {
+            if (dst) ((float *)dst)[t] = trk[t].z_height;
+            else trk[t].z_height = ((const float *)src)[t];
+        }
+        break;
+    case MOC_ARR_P_WEIGHT:
+        for (long t = 0; t < T3; t++) {
+            if (dst) ((float *)dst)[t] = trk[t].p_weight;
+            else trk[t].p_weight = ((const float *)src)[t];
+        }
+        break;
+    case MOC_HOST_AZ_WEIGHT:
+        for (long i = 0; i < T2; i++) {
+            if (dst) ((float *)dst)[i] = p->tracks_2D[i].az_weight;
+            else p->tracks_2D[i].az_weight = ((const float *)src)[i];
+        }
+        break;
+    case MOC_HOST_N_SEGMENTS:
+        if (!dst) { moc_set_error("n_segments is read-only"); return MOC_EINVAL; }
+        for (long i = 0; i < T2; i++) ((long *)dst)[i] = p->tracks_2D[i].n_segments;
+        break;
+    case MOC_HOST_SEG_LENGTHS: {
+        long e = 0;
+        for (long i = 0; i < T2; i++)
+            for (long k = 0; k < p->tracks_2D[i].n_segments; k++, e++) {
+                if (dst) ((float *)dst)[e] = p->tracks_2D[i].segments[k].length;
+                else p->tracks_2D[i].segments[k].length = ((const float *)src)[e];
+            }
+        break;
+    }
+    case MOC_HOST_XS_INDEX:
+        if (!dst) { moc_set_error("xs_index is read-only"); return MOC_EINVAL; }
+        for (long i = 0; i < N; i++)
+            ((int *)dst)[i] = (int)((p->sources[i].XS[0] - s0->XS[0]) / (3 * G));
+        break;
+    case MOC_HOST_VOL:
+        for (long i = 0; i < N; i++) {
+            if (dst) ((float *)dst)[i] = p->sources[i].vol;
+            else p->sources[i].vol = ((const float *)src)[i];
+        }
+        break;
+    }
+    return (long)n;
+}
+
+long moc_params_get(const Input *in, const Params *p, int which, void *dst, size_t bytes)
+{
+    return params_copy(in, p, which, dst, NULL, bytes);
+}
+
+long moc_params_set(const Input *in, Params *p, int which, const void *src, size_t bytes)
+{
+    return params_copy(in, p, which, NULL, src, bytes);
+}

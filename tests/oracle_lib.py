@@ -184,7 +184,7 @@ class OracleCase(_Base):
                 getattr(L, "oracle_" + n).argtypes = [C.c_void_p]
             for n in ("psi", "source_data", "xs_data", "scatter_data", "polar_angles",
                       "p_weight", "z_height", "az_weight", "n_segments", "seg_lengths",
-                      "xs_index", "vol", "table_values", "leakage", "seg_count", "digest",
+                      "xs_index", "vol", "table_values", "leakage", "seg_count", "digest", "abs_flux",
                       "trace_track", "trace_row", "trace_ds", "trace_zstart"):
                 getattr(L, "oracle_" + n).restype = C.c_void_p
                 getattr(L, "oracle_" + n).argtypes = [C.c_void_p]
@@ -276,6 +276,11 @@ class OracleCase(_Base):
     @property
     def seg_count(self):
         return _view(self._ptr("seg_count"), (self.I.ntracks,), np.uint32)
+
+    @property
+    def abs_flux(self):
+        I = self.I
+        return _view(self._ptr("abs_flux"), (I.n_source_regions_per_node, I.fai, I.n_egroups))
 
     @property
     def digest(self):
@@ -462,6 +467,15 @@ def rel_l2(a, b):
     b = np.asarray(b, np.float64).ravel()
     d = np.linalg.norm(b)
     return float(np.linalg.norm(a - b) / d) if d > 0 else float(np.linalg.norm(a - b))
+
+
+def noise_units(a, b, magnitude):
+    """|a-b| in units of FP32 epsilon times the accumulation magnitude of each element
+    (backward-error view of a sum whose terms cancel)."""
+    a = np.asarray(a, np.float64).ravel()
+    b = np.asarray(b, np.float64).ravel()
+    mag = np.maximum(np.asarray(magnitude, np.float64).ravel(), 1e-300)
+    return np.abs(a - b) / (np.finfo(np.float32).eps * mag)
 
 
 def frac_within(a, b, tol):
