@@ -1,0 +1,482 @@
+#!/usr/bin/env python
+"""bench.py -- segment-group integrations/sec of the 3D MOC transport sweep on B200.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl moc|reference]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" is one iteration of the reference's loop (reference src/main.c:57-92) over one
+spatial domain per GPU: transport_sweep -> [fast_transfer_boundary_fluxes when N > 1] ->
+renormalize_flux -> update_sources -> compute_keff.  The metric is the reference's own
+(src/utils.c:147-155): integrations = segments_processed * n_egroups; `value` is the
+whole-job integrations per second of step time (all N domains; weak scaling: every rank owns
+a full-size domain, exactly as every MPI rank of the reference does).
+
+Workload at N = 1: the default strawman problem (BASELINE.json configs[1]): the built-in
+defaults of set_default_input (src/init.c:33-74; G=104, 120 2D segments per track,
+15.5 M 3D tracks, 12.9 GB of angular flux, ~1.93e9 3D segments = 2.0e11 integrations per
+sweep).  `--workload default_in` runs the shipped default.in values instead (G=100, 20
+segments per track); `--workload small` the -s problem.
+
+The JSON line also carries
+  e2e          the same metric through the reference's own entry point
+               transport_sweep(Params*, Input*) on HOST structures: every step uploads the
+               mutable state from pinned host memory and downloads what the reference
+               function mutates (inside the timed region)
+  roofline     the attenuation kernel (the dominant launch) against measured HBM bandwidth,
+               plus its FP32 and L2-level rates (what actually bounds it)
+  cpu_baseline the UNMODIFIED reference (oracle/_ref, OpenMP, all host cores) timed here on
+               a bounded sample of the same workload (N = 1 only)
+  clocks       SM clocks / throttle reasons sampled with nvidia-smi during the timed region
+
+`--impl reference` times the reference's own CPU implementation (oracle/_ref OpenMP build;
+falls back to the serial C restatement oracle/_build when the reference library did not
+travel) -- the only place this file touches oracle/.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "segment-group integrations/sec"
+UNIT = "integrations/s"
+FLOP_PER_INTEGRATION = 62      # attenuate_fluxes as written, axial_exp = 2
+L2_BYTES_PER_INTEGRATION = 24  # 3 source rows + sigT (16 B gathered) + 8 B tally read-modify-write
+FP32_PEAK_TFLOPS_NOMINAL = 148 * 128 * 2 * 1.965e9 / 1e12   # 74.4: 148 SMs x 128 FMA lanes x 1965 MHz
+
+# values of the shipped default.in (reference src/default.in:1-18), in input-file order
+DEFAULT_IN = [17, 17, 9, 5, 2, 0.05, 0.25, 64, 10, 100, 1, 20, 20, 21.42, 400.0, 0.01, 5000, 0]
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="moc", choices=["moc", "reference"])
+    ap.add_argument("--workload", default="default", choices=["default", "default_in", "small"])
+    ap.add_argument("--exp", default="table", choices=["table", "sfu"],
+                    help="table = the reference's exponential table (parity mode, default); "
+                         "sfu = MUFU.EX2 (__expf)")
+    ap.add_argument("--limit-tracks-2d", type=int, default=0,
+                    help="shrink the number of 2D tracks (profiling under ncu only; not a bench value)")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0,
+                    help="target CPU time of the cpu_baseline sample")
+    ap.add_argument("--grid", default="", help="cx,cy,cz (default: 1x1x1, 2x1x1, 2x2x1, 2x2x2)")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------ helpers
+
+def workload_input(m, name):
+    if name == "default":
+        inp = m.default_input()
+        label = ("default strawman problem, built-in set_default_input (src/init.c:33-74): "
+                 "G=104, 120 2D segments/track")
+    elif name == "default_in":
+        inp = m.input_from_values(DEFAULT_IN)
+        label = "default.in as shipped (src/default.in): G=100, cai=9, 20 2D segments/track"
+    else:
+        inp = m.small_input()
+        label = "small problem (-s, src/init.c:77-103)"
+    return inp, label
+
+
+def grid_for(n, spec):
+    if spec:
+        cx, cy, cz = (int(v) for v in spec.split(","))
+    else:
+        cx, cy, cz = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}.get(n, (n, 1, 1))
+    assert cx * cy * cz == n, f"grid {cx}x{cy}x{cz} does not have {n} domains"
+    return cx, cy, cz
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(prefix="moc_clocks_", suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        with open(self.path) as f:
+            for line in f:
+                parts = [p.strip() for p in line.split(",")]
+                if len(parts) < 7:
+                    continue
+                try:
+                    sm.append(float(parts[0])); mx.append(float(parts[1])); pw.append(float(parts[2]))
+                except ValueError:
+                    continue
+                for n, v in zip(names, parts[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+        os.unlink(self.path)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "power_w_max": max(pw),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------ the reference on the host cores
+
+class ReferenceCPU:
+    """oracle/_ref/libsimplemoc_ref_omp.so: the unmodified reference, stock OpenMP flags."""
+
+    def __init__(self):
+        path = os.path.join(ROOT, "oracle", "_ref", "libsimplemoc_ref_omp.so")
+        self.kind = "reference"
+        if not os.path.exists(path):
+            raise FileNotFoundError(path)
+        L = C.CDLL(path, mode=C.RTLD_LOCAL)
+        L.ref_case_create.restype = C.c_void_p
+        L.ref_case_create.argtypes = [C.c_char_p, C.c_int, C.c_uint64, C.c_int, C.c_long]
+        L.ref_case_destroy.argtypes = [C.c_void_p]
+        L.ref_time_transport_sweep.restype = C.c_double
+        L.ref_time_transport_sweep.argtypes = [C.c_void_p]
+        L.ref_input.restype = C.c_void_p
+        L.ref_input.argtypes = [C.c_void_p]
+        L.ref_psi.restype = C.c_void_p
+        L.ref_psi.argtypes = [C.c_void_p]
+        L.ref_source_data.restype = C.c_void_p
+        L.ref_source_data.argtypes = [C.c_void_p]
+        self.L = L
+
+    def make(self, workload, nthreads, limit_tracks_2d):
+        from simplemoc_b200.api import Input
+        path = b""
+        tmp = None
+        if workload == "default_in":
+            fd, tmp = tempfile.mkstemp(prefix="moc_ref_", suffix=".in")
+            with os.fdopen(fd, "w") as f:
+                for v in DEFAULT_IN:
+                    f.write(f"{v}\n")
+            path = tmp.encode()
+        h = self.L.ref_case_create(path, int(workload == "small"), 1, nthreads, limit_tracks_2d)
+        if tmp:
+            os.unlink(tmp)
+        inp = C.cast(self.L.ref_input(h), C.POINTER(Input)).contents
+        return h, inp
+
+    def reset(self, h, inp):
+        """zero the angular and scalar flux (what a fresh run starts from), outside any timed region"""
+        T3, G, F, N = inp.ntracks, inp.n_egroups, inp.fai, inp.n_source_regions_per_node
+        C.memset(self.L.ref_psi(h), 0, 4 * 2 * T3 * G)
+        C.memset(self.L.ref_source_data(h) + 4 * N * F * G, 0, 4 * N * F * G)
+
+    def sweep_seconds(self, h):
+        return self.L.ref_time_transport_sweep(h)
+
+    def destroy(self, h):
+        self.L.ref_case_destroy(h)
+
+
+def time_reference(args, steps, warmup, seconds_per_step):
+    """Times transport_sweep of the reference on a sample of `workload` sized for
+    ~seconds_per_step; returns (integrations/s, description dict)."""
+    ref = ReferenceCPU()
+    cores = os.cpu_count() or 1
+    # calibrate on a sliver
+    probe_tracks = 16
+    h, inp = ref.make(args.workload, cores, probe_tracks)
+    t = ref.sweep_seconds(h)
+    integ = inp.segments_processed * inp.n_egroups
+    ref.destroy(h)
+    rate = integ / max(t, 1e-6)
+    per_2d_track = integ / probe_tracks
+    want = int(max(16, seconds_per_step * rate / per_2d_track)) // 2 * 2
+    h, inp = ref.make(args.workload, cores, want)
+    want = inp.ntracks_2D   # clipped to the full problem if the sample would exceed it
+    times, integs = [], []
+    for s in range(warmup + steps):
+        ref.reset(h, inp)
+        t = ref.sweep_seconds(h)
+        if s >= warmup:
+            times.append(t)
+            integs.append(inp.segments_processed * inp.n_egroups)
+    ref.destroy(h)
+    total_t, total_i = sum(times), sum(integs)
+    desc = {"kind": ref.kind, "cores": cores,
+            "sample": f"transport_sweep of the unmodified reference (OpenMP, -Ofast) over "
+                      f"{want} of the workload's 2D tracks ({integs[0]:.3e} integrations/step, "
+                      f"{total_t / len(times):.2f} s/step, {len(times)} steps after {warmup} warm-up)",
+            "value": total_i / total_t, "unit": UNIT,
+            "ns_per_integration": 1e9 * total_t / total_i}
+    return total_i / total_t, total_t / len(times), desc
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    # the whole run should end within a few minutes
+    per_step = max(2.0, min(20.0, 150.0 / (args.steps + args.warmup)))
+    value, sec_per_step, desc = time_reference(args, args.steps, args.warmup, per_step)
+    import simplemoc_b200 as m
+    _, label = workload_input(m, args.workload)
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * sec_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": label, "sampled": True}, "impl": "reference",
+            "ns_per_integration": 1e9 / value, "cpu_baseline": desc,
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------ the CUDA path
+
+def run_moc(args):
+    import torch
+    import simplemoc_b200 as m
+    from simplemoc_b200 import api
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit(f"--gpus {args.gpus} needs `python -m torch.distributed.run "
+                             f"--nproc-per-node {args.gpus} bench.py ...` (one process per GPU)")
+        raise SystemExit(f"WORLD_SIZE={world} but --gpus {args.gpus}")
+    if not torch.cuda.is_available() or api.device_count() == 0:
+        raise SystemExit("bench.py: no CUDA device -- the MOC path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    inp, label = workload_input(m, args.workload)
+    inp.mype = rank
+    inp = m.derive(inp, args.limit_tracks_2d)
+    t0 = time.time()
+    host = m.HostProblem(inp, seed=1 + rank)          # every rank: a full-size domain of its own
+    dev = m.DeviceProblem(host, device=local,
+                          exp_mode=api.EXP_SFU if args.exp == "sfu" else api.EXP_TABLE_REF)
+    build_s = time.time() - t0
+    cx, cy, cz = grid_for(world, args.grid)
+    grid = m.make_grid(cx, cy, cz, rank)
+    if world > 1:
+        # the 128-byte NCCL id travels over torch.distributed; the exchange itself is the library's
+        buf = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            buf.copy_(torch.frombuffer(bytearray(api.nccl_unique_id()), dtype=torch.uint8))
+        dist.broadcast(buf, 0)
+        dev.comm_init(world, rank, bytes(buf.cpu().numpy().tobytes()))
+
+    stream = torch.cuda.ExternalStream(dev.stream, device=torch.device("cuda", local))
+    G = inp.n_egroups
+    state = {"keff": 1.0, "segments": 0, "att_ms": 0.0, "fill_ms": 0.0, "count_ms": 0.0, "sweep_ms": 0.0}
+
+    def step(accumulate):
+        n = dev.sweep()
+        if world > 1:
+            dev.exchange(grid)
+        dev.renormalize()
+        dev.update_sources(state["keff"])
+        state["keff"] = dev.compute_keff()
+        if accumulate:
+            t = dev.timing()
+            state["segments"] += n
+            state["att_ms"] += t.attenuate_ms
+            state["fill_ms"] += t.fill_ms
+            state["count_ms"] += t.count_ms
+            state["sweep_ms"] += t.total_ms
+        return n
+
+    for _ in range(args.warmup):
+        step(False)
+    sampler = ClockSampler(local)
+    barrier(); torch.cuda.synchronize()
+    if rank == 0:
+        sampler.start()
+    launches0 = dev.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step(True)
+    e1.record(stream)
+    torch.cuda.synchronize(); barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = e0.elapsed_time(e1)
+    launches = dev.launch_count - launches0
+    segs = state["segments"]
+    if dist is not None:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        s = torch.tensor([segs, launches], dtype=torch.int64, device="cuda")
+        dist.all_reduce(s, op=dist.ReduceOp.SUM)
+        segs, launches = int(s[0].item()), int(s[1].item())
+    integrations = segs * G
+    value = integrations / (ms * 1e-3)
+
+    # ---- end to end through the reference's own entry point on host structures (rank-local)
+    e2e = None
+    if not args.no_e2e:
+        e2e = measure_e2e(args, m, api, host, dev, torch, dist, world, rank, local)
+
+    # ---- roofline of the dominant kernel (attenuate_kernel), per launch
+    att_s = state["att_ms"] * 1e-3
+    my_integ = state["segments"] * G
+    T3 = inp.ntracks
+    n_launch = max(args.steps, 1)
+    # algorithmic HBM bytes of one launch: angular flux in and out once, segment records in,
+    # per-track offsets/counts/weights in (the gathered source rows live in L2)
+    hbm_bytes = (2 * 4 * T3 * G + 12 * (state["segments"] / n_launch) + 12 * T3)
+    hbm_peak, peak_src = measured_peaks()
+    att_per_launch = att_s / n_launch
+    roof = {"kernel": "attenuate_kernel", "bound": "hbm",
+            "achieved": hbm_bytes / att_per_launch / 1e9 if att_per_launch > 0 else None,
+            "peak": hbm_peak, "unit": "GB/s", "peak_source": peak_src, "traffic": None,
+            "ms_per_launch": 1e3 * att_per_launch, "share_of_step": state["att_ms"] / ms if ms else None,
+            "fp32": {"achieved_tflops": my_integ * FLOP_PER_INTEGRATION / att_s / 1e12 if att_s else None,
+                     "peak_tflops_nominal": FP32_PEAK_TFLOPS_NOMINAL,
+                     "flop_per_integration": FLOP_PER_INTEGRATION},
+            "l2": {"achieved_gbs": my_integ * L2_BYTES_PER_INTEGRATION / att_s / 1e9 if att_s else None,
+                   "bytes_per_integration": L2_BYTES_PER_INTEGRATION},
+            "note": "not HBM-bound: FP32 issue + L2 gather/atomic bound (DESIGN.md 'roofline')"}
+    roof["frac"] = roof["achieved"] / hbm_peak if roof["achieved"] else None
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            _, _, cpu = time_reference(args, 1, 0, args.cpu_seconds)
+        except FileNotFoundError as e:
+            cpu = {"unavailable": f"{e} (oracle/_ref did not travel)"}
+
+    if dist is not None:
+        dist.barrier()
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": label, "domains": f"{cx}x{cy}x{cz}", "exp": args.exp,
+                           "step": "transport_sweep" + (" + boundary exchange" if world > 1 else "") +
+                                   " + renormalize_flux + update_sources + compute_keff",
+                           "ntracks_per_gpu": T3, "n_egroups": G,
+                           "segments_per_sweep_per_gpu": state["segments"] // n_launch,
+                           "l2": "inputs larger than L2 (12.9 GB angular flux + 23 GB segment records "
+                                 "streamed per step); no flush",
+                           "host_build_s": round(build_s, 1)},
+                "ns_per_integration": 1e9 / value, "keff": state["keff"],
+                "sweep_ms": state["sweep_ms"] / n_launch,
+                "phases_ms": {"count": state["count_ms"] / n_launch, "fill": state["fill_ms"] / n_launch,
+                              "attenuate": state["att_ms"] / n_launch},
+                "gpu_launches": launches, "clocks": clocks, "roofline": roof, "e2e": e2e,
+                "cpu_baseline": cpu}
+        if args.limit_tracks_2d:
+            line["config"]["limit_tracks_2d"] = args.limit_tracks_2d
+        print(json.dumps(line), flush=True)
+    dev.close()
+    host.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def measure_e2e(args, m, api, host, dev, torch, dist, world, rank, local):
+    """transport_sweep(Params*, Input*) -- the reference's own prototype (src/solver.c:283) --
+    on the host structures, non-resident: upload of the step's inputs from pinned host memory,
+    the sweep, download of what transport_sweep mutates; all inside the timed region."""
+    L = api.lib()
+    inp = host.I
+    T3, G, F, N = inp.ntracks, inp.n_egroups, inp.fai, inp.n_source_regions_per_node
+    # release the resident copy first: the drop-in path builds its own mirror of this Params
+    dev.close()
+    L.moc_set_resident(0)
+    L.moc_dropin_configure(host.seed, host.rand_calls, 1 if args.exp == "sfu" else 0, 48)
+    steps = max(1, args.e2e_steps)
+    I2 = type(inp).from_buffer_copy(inp)
+    L.transport_sweep(C.byref(host.P), C.byref(I2))           # warm-up: builds the mirror
+    torch.cuda.synchronize()
+    mirror = L.moc_handle_of(C.byref(host.P))
+    stream = torch.cuda.ExternalStream(L.moc_get_stream(mirror), device=torch.device("cuda", local))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if dist is not None:
+        dist.barrier()
+    t0 = time.perf_counter()
+    e0.record(stream)
+    segs = 0
+    for _ in range(steps):
+        L.transport_sweep(C.byref(host.P), C.byref(I2))       # returns after the download completed
+        segs += I2.segments_processed
+    e1.record(stream)
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    dt = e0.elapsed_time(e1) * 1e-3
+    if dist is not None:
+        t = torch.tensor([dt, wall], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt, wall = float(t[0].item()), float(t[1].item())
+        s = torch.tensor([segs], dtype=torch.int64, device="cuda")
+        dist.all_reduce(s, op=dist.ReduceOp.SUM)
+        segs = int(s.item())
+    h2d = 40 * T3 + 4 * T3 * G + 4 * (2 * F + 1) * N * G     # Track image, forward flux rows, source slab
+    d2h = 40 * T3 + 4 * T3 * G + 4 * F * N * G               # Track image, forward flux rows, scalar flux
+    L.moc_release(C.byref(host.P))
+    return {"value": segs * G / dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+            "steps": steps, "ms_per_step": 1e3 * dt / steps, "host_wall_ms_per_step": 1e3 * wall / steps,
+            "call": "transport_sweep(Params*, Input*) on host structures (drop-in C-ABI), CUDA events on "
+                    "the library's stream around upload + sweep + download"}
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_moc(args)
+
+
+if __name__ == "__main__":
+    main()

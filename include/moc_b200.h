@@ -237,6 +237,10 @@ int moc_download(moc_handle *h, Params *P);   /* device -> host structures      
 int moc_upload(moc_handle *h, const Params *P); /* host structures -> device (mutable state) */
 float moc_get_leakage(moc_handle *h);
 int moc_synchronize(moc_handle *h);
+/* the cudaStream_t every kernel of this handle is launched on (for CUDA-event timing by the caller) */
+void *moc_get_stream(moc_handle *h);
+/* kernels launched through this handle since moc_create (the library counts its own launches) */
+long moc_get_launch_count(moc_handle *h);
 
 /* multi-GPU: one process per GPU, one spatial domain per process.  The caller
  * distributes the 128-byte NCCL unique id (e.g. with torch.distributed). */
@@ -245,6 +249,19 @@ int moc_comm_init(moc_handle *h, int nranks, int rank, const char id[128]);
 /* neighbour table of a cx*cy*cz non-periodic Cartesian grid with MPI_Cart_shift
  * semantics (src/init.c:162-225; the reference hard-codes 2x2x1) */
 int moc_make_grid(int cx, int cy, int cz, int rank, CommGrid *out);
+/* The schedule of fast_transfer_boundary_fluxes (src/comms.c:12-28,75-183) for one rank, in the
+ * reference's (round, direction) order: operation k covers `count` floats of the flux slab at
+ * `offset`; they are sent to send_to (or, at a border, -1: pairwise-summed into the leakage,
+ * src/comms.c:118-121) and replaced by what recv_from sent from the same offset of its own slab
+ * (or, at a border, -1: by zeros, src/comms.c:146-149,179-181).  Pure host arithmetic: usable
+ * without a GPU.  Returns the number of operations (ops may be NULL to query it), or MOC_EINVAL
+ * if the plan does not fit the slab. */
+typedef struct {
+    long long offset, count;
+    int round, direction;      /* direction: 0 x+, 1 x-, 2 y+, 3 y-, 4 z+, 5 z-  (src/comms.c:53-71) */
+    int send_to, recv_from;
+} moc_exchange_op;
+long moc_exchange_plan(const Input *I, const CommGrid *grid, moc_exchange_op *ops, long max_ops);
 
 const char *moc_last_error(void);
 int moc_device_count(void);

@@ -12,7 +12,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libmoc_b200.so")
+# MOC_B200_LIB: an alternative build of the same library (kernel tuning experiments)
+LIB_PATH = os.environ.get("MOC_B200_LIB") or os.path.join(HERE, "libmoc_b200.so")
 
 
 class MocError(RuntimeError):
@@ -83,7 +84,7 @@ EXPORTED = [
     "moc_create", "moc_destroy", "moc_set_option", "moc_get_option", "moc_sweep",
     "moc_renormalize", "moc_update_sources", "moc_compute_keff", "moc_exchange",
     "moc_get_sweep_timing", "moc_get_array", "moc_set_array", "moc_download", "moc_upload",
-    "moc_get_leakage", "moc_synchronize", "moc_comm_get_unique_id", "moc_comm_init",
+    "moc_get_leakage", "moc_synchronize", "moc_get_stream", "moc_get_launch_count", "moc_comm_get_unique_id", "moc_comm_init",
     "moc_make_grid", "moc_last_error", "moc_device_count", "moc_set_default_input",
     "moc_set_small_input", "moc_read_input_file", "moc_read_CLI",
     "moc_calculate_derived_inputs", "moc_est_mem_usage", "moc_build_tracks",
@@ -138,6 +139,10 @@ def lib():
     L.moc_get_leakage.restype = C.c_float
     L.moc_get_leakage.argtypes = [vp]
     L.moc_synchronize.argtypes = [vp]
+    L.moc_get_stream.restype = vp
+    L.moc_get_stream.argtypes = [vp]
+    L.moc_get_launch_count.restype = C.c_long
+    L.moc_get_launch_count.argtypes = [vp]
     L.moc_comm_get_unique_id.argtypes = [C.c_char_p]
     L.moc_comm_init.argtypes = [vp, C.c_int, C.c_int, C.c_char_p]
     L.moc_make_grid.argtypes = [C.c_int] * 4 + [C.POINTER(CommGrid)]
@@ -323,6 +328,18 @@ class DeviceProblem:
     @property
     def leakage(self):
         return lib().moc_get_leakage(self.h)
+
+    @property
+    def stream(self):
+        """cudaStream_t (as int) the kernels of this problem are launched on"""
+        return lib().moc_get_stream(self.h)
+
+    @property
+    def launch_count(self):
+        return lib().moc_get_launch_count(self.h)
+
+    def synchronize(self):
+        _check(lib().moc_synchronize(self.h), "moc_synchronize")
 
     def _shape(self, which):
         I = self.I

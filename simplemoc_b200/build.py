@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(ROOT, "include")
-LIB = os.path.join(HERE, "libmoc_b200.so")
+LIB = os.path.join(HERE, "libmoc_b200.so")   # experiments: build_lib(out=..., extra_nvcc=[...])
 DRIVER = os.path.join(HERE, "SimpleMOC-b200")
 
 NVCC = os.environ.get("NVCC") or shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
@@ -33,19 +33,20 @@ def _run(cmd, verbose):
     subprocess.check_call(cmd)
 
 
-def build_lib(force=False, verbose=False, extra_nvcc=()):
+def build_lib(force=False, verbose=False, extra_nvcc=(), out=None):
     srcs = [os.path.join(CSRC, f) for f in
             ("moc_device.cu", "moc_kernels.cuh", "moc_host.c", "moc_internal.h")]
     srcs += [os.path.join(INCLUDE, f) for f in ("moc_b200.h", "moc_rng.h")]
-    if not force and not _newer(LIB, srcs):
-        return LIB
+    out = out or LIB
+    if not force and not _newer(out, srcs):
+        return out
     obj = os.path.join(CSRC, "moc_host.o")
     _run([GCC, "-std=gnu99", "-O2", "-ffp-contract=off", "-fPIC", "-Wall", "-I", INCLUDE, "-I", CSRC,
           "-c", os.path.join(CSRC, "moc_host.c"), "-o", obj], verbose)
     _run([NVCC, *ARCH, "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-shared",
           "-I", INCLUDE, "-I", CSRC, *extra_nvcc,
-          os.path.join(CSRC, "moc_device.cu"), obj, "-o", LIB, "-ldl"], verbose)
-    return LIB
+          os.path.join(CSRC, "moc_device.cu"), obj, "-o", out, "-ldl"], verbose)
+    return out
 
 
 def build_driver(force=False, verbose=False):

@@ -132,17 +132,23 @@ struct moc_handle {
     long long batch_segments = 0;  // 0 = choose from free memory
     int source_stride = 48;
     int lanes_override = 0;
+    int fast_cell_ok = 0;          // table_cell_check_kernel found no mismatch (see moc_kernels.cuh)
     int want_digest = 0;
     // scratch capacity
     long long rec_capacity = 0, off_capacity = 0;
     std::vector<unsigned long long> pair_base_host;
     unsigned long long *pair_base_pinned = nullptr;
     moc_sweep_timing timing;
+    mutable long launch_count = 0;   // kernels launched through this handle
     float leakage_host = 0.f;
     // comms
     void *nccl_comm = nullptr;
     int nranks = 1, rank = 0;
     float *recv_stage = nullptr;
+    long stage_chunks = 0;
+    long long *exch_table = nullptr;
+    float *exch_sums = nullptr;
+    long exch_capacity = 0;
     cudaStream_t comm_stream = nullptr;
 };
 
@@ -319,6 +325,21 @@ static int upload_static(moc_handle *h, const Params *P, const HostLayout &L)
     h->table_n = P->expTable.N;
     if ((rc = dev_alloc(&h->d.table, (size_t)2 * h->table_n))) return rc;
     CUDA_TRY(cudaMemcpy(h->d.table, P->expTable.values, sizeof(float) * 2 * (size_t)h->table_n, cudaMemcpyHostToDevice));
+
+    // May the attenuation kernel pick table cells with the 3-instruction division?  Only if it
+    // agrees with the IEEE division for every float the table can be asked about.
+    {
+        unsigned long long *bad = nullptr, bad_host = 1;
+        CUDA_TRY(cudaMalloc((void **)&bad, sizeof(unsigned long long)));
+        CUDA_TRY(cudaMemset(bad, 0, sizeof(unsigned long long)));
+        unsigned int bits_max;
+        const float x_max = h->table_max;
+        memcpy(&bits_max, &x_max, sizeof bits_max);
+        table_cell_check_kernel<<<148 * 16, 256>>>(bits_max, h->table_dx, 1.0f / h->table_dx, 0.5f * h->table_dx, bad);
+        CUDA_TRY(cudaMemcpy(&bad_host, bad, sizeof bad_host, cudaMemcpyDeviceToHost));
+        cudaFree(bad);
+        h->fast_cell_ok = (bad_host == 0 && x_max > 0.f);
+    }
     return MOC_OK;
 }
 
@@ -353,6 +374,8 @@ extern "C" int moc_destroy(moc_handle *h)
         if (e) cudaEventDestroy(e);
     if (h->pair_base_pinned) cudaFreeHost(h->pair_base_pinned);
     if (h->recv_stage) cudaFree(h->recv_stage);
+    if (h->exch_table) cudaFree(h->exch_table);
+    if (h->exch_sums) cudaFree(h->exch_sums);
     if (h->comm_stream) cudaStreamDestroy(h->comm_stream);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -478,6 +501,9 @@ extern "C" int moc_set_option(moc_handle *h, int option, long value)
         h->lanes_override = (int)value;
         return MOC_OK;
     case 100: h->want_digest = value != 0; return MOC_OK;   // MOC_OPT_DIGEST (diagnostic)
+    case 101:                                                // MOC_OPT_EXACT_DIV (diagnostic): 1 = never use the fast cell selection
+        if (value) h->fast_cell_ok = 0;
+        return MOC_OK;
     }
     moc_set_error("moc_set_option: bad option %d / value %ld", option, value);
     return MOC_EINVAL;
@@ -494,6 +520,7 @@ extern "C" long moc_get_option(moc_handle *h, int option)
     case MOC_OPT_SOURCE_STRIDE: return h->source_stride;
     case MOC_OPT_LANES_PER_TRACK: return h->lanes_override;
     case 100: return h->want_digest;
+    case 101: return !h->fast_cell_ok;
     }
     return -1;
 }
@@ -548,6 +575,7 @@ static void launch_walk(const moc_handle *h, const WalkParams &w, long long n_pa
     int threads = ((Z + kpt - 1) / kpt + 31) / 32 * 32;
     if (threads > 1024) threads = 1024;
     const unsigned grid = (unsigned)n_pairs;
+    h->launch_count++;
     switch (kpt) {
     case 1: stack_walk_kernel<1, FILL><<<grid, threads, 0, h->stream>>>(w); break;
     case 2: stack_walk_kernel<2, FILL><<<grid, threads, 0, h->stream>>>(w); break;
@@ -588,11 +616,21 @@ static LaneMap choose_lanes(int G, int lanes_override)
 template <int L, int NV4, int NS>
 static int launch_attenuate_mode(const moc_handle *h, const AttenuateParams &a, unsigned grid, size_t smem)
 {
-    const bool sfu = h->exp_mode == 1, flat = h->I.axial_exp == 0;
-    if (!sfu && !flat) attenuate_kernel<L, NV4, NS, false, false><<<grid, 128, smem, h->stream>>>(a);
-    else if (sfu && !flat) attenuate_kernel<L, NV4, NS, true, false><<<grid, 128, 0, h->stream>>>(a);
-    else if (!sfu && flat) attenuate_kernel<L, NV4, NS, false, true><<<grid, 128, smem, h->stream>>>(a);
-    else attenuate_kernel<L, NV4, NS, true, true><<<grid, 128, 0, h->stream>>>(a);
+    const bool flat = h->I.axial_exp == 0;
+    // 0: table, IEEE division; 1: table, verified fast division; 2: SFU
+    const int mode = h->exp_mode == 1 ? 2 : (h->fast_cell_ok ? 1 : 0);
+    h->launch_count++;
+#define MOC_LAUNCH(M, F) attenuate_kernel<L, NV4, NS, M, F><<<grid, 128, (M) == 2 ? 0 : smem, h->stream>>>(a)
+    if (!flat) {
+        if (mode == 0) MOC_LAUNCH(0, false);
+        else if (mode == 1) MOC_LAUNCH(1, false);
+        else MOC_LAUNCH(2, false);
+    } else {
+        if (mode == 0) MOC_LAUNCH(0, true);
+        else if (mode == 1) MOC_LAUNCH(1, true);
+        else MOC_LAUNCH(2, true);
+    }
+#undef MOC_LAUNCH
     return MOC_OK;
 }
 
@@ -606,7 +644,7 @@ static int launch_attenuate(const moc_handle *h, const AttenuateParams &a, long 
     }
     const int tracks_per_block = 4 * (32 / m.L);
     const unsigned grid = (unsigned)((n_tracks + tracks_per_block - 1) / tracks_per_block);
-    const size_t smem = sizeof(float2) * (size_t)h->table_n;
+    const size_t smem = sizeof(float2) * ((size_t)h->table_n + 1);
 #define MOC_CASE(l, v, s) \
     if (m.L == l && m.NV4 == v && m.NS == s) return launch_attenuate_mode<l, v, s>(h, a, grid, smem);
     MOC_CASE(8, 3, 1)
@@ -677,6 +715,7 @@ extern "C" int moc_sweep(moc_handle *h, long *segments_processed)
     launches++;
     CUDA_TRY(cudaEventRecord(e_count, h->stream));
     pair_scan_kernel<<<1, 1024, 0, h->stream>>>(h->d.pair_count, h->d.pair_base, pairs);
+    h->launch_count++;
     launches++;
     CUDA_TRY(cudaMemcpyAsync(h->pair_base_pinned, h->d.pair_base, sizeof(unsigned long long) * (size_t)(pairs + 1),
                              cudaMemcpyDeviceToHost, h->stream));
@@ -688,7 +727,9 @@ extern "C" int moc_sweep(moc_handle *h, long *segments_processed)
 
     // ---- batches of whole stacks whose records fit the staging buffers
     long long cap = h->batch_segments;
-    if (cap <= 0) {
+    if (cap <= 0 && (long long)total <= h->rec_capacity) {
+        cap = h->rec_capacity;   // the staging buffers of the previous sweep are large enough
+    } else if (cap <= 0) {
         size_t free_b = 0, total_b = 0;
         CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
         free_b += (size_t)h->rec_capacity * 12;   // what we already hold can be reused
@@ -703,7 +744,10 @@ extern "C" int moc_sweep(moc_handle *h, long *segments_processed)
         moc_set_error("a single z-stack produces %llu segments (> 2^32)", largest_pair);
         return MOC_EINVAL;
     }
-    const long long need = (long long)std::min<unsigned long long>(total, (unsigned long long)cap);
+    // 2 % headroom: the segment count drifts from sweep to sweep (stale ray heights, solver.c:514-523)
+    // and re-allocating multi-GB staging buffers costs hundreds of milliseconds
+    long long need = (long long)std::min<unsigned long long>(total + total / 50 + 1024, (unsigned long long)cap);
+    if (need > (1ll << 32) - 1) need = (1ll << 32) - 1;
     // the largest batch in tracks
     std::vector<std::pair<long long, long long>> batches;
     {
@@ -740,6 +784,7 @@ extern "C" int moc_sweep(moc_handle *h, long *segments_processed)
     a.sigT = h->d.src + (size_t)2 * h->N * h->F * h->G;
     a.table = h->d.table;
     a.table_dx = h->table_dx;
+    a.table_rdx = 1.0f / h->table_dx;
     a.table_max = h->table_max;
     a.table_half_dx = 0.5f * h->table_dx;
     a.table_n = h->table_n;
@@ -841,6 +886,7 @@ extern "C" int moc_renormalize(moc_handle *h)
     const long long n4 = n / 4;
     scale_psi_kernel<<<148 * 8, 256, 0, h->stream>>>(reinterpret_cast<float4 *>(h->d.psi), n4, h->d.psi + 4 * n4,
                                                     (int)(n - 4 * n4), h->d.scalars);
+    h->launch_count += 4;
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     return MOC_OK;
@@ -859,6 +905,7 @@ extern "C" int moc_update_sources(moc_handle *h, float keff, float *res)
     region_fold_kernel<<<(unsigned)((h->N + 127) / 128), 128, 0, h->stream>>>(h->d.per_fine, h->N, h->F,
                                                                              h->d.per_region_a);
     pairwise_reduce_kernel<<<1, 256, 0, h->stream>>>(h->d.per_region_a, h->N, h->d.scalars, 1);
+    h->launch_count += 3;
     CUDA_TRY(cudaGetLastError());
     float r = 0.f;
     CUDA_TRY(cudaMemcpyAsync(&r, h->d.scalars + 1, sizeof(float), cudaMemcpyDeviceToHost, h->stream));
@@ -876,6 +923,7 @@ extern "C" int moc_compute_keff(moc_handle *h, float *keff)
                                                                                        h->d.per_region_b);
     pairwise_reduce_kernel<<<1, 256, 0, h->stream>>>(h->d.per_region_a, h->N, h->d.scalars, 2);   // absorption
     pairwise_reduce_kernel<<<1, 256, 0, h->stream>>>(h->d.per_region_b, h->N, h->d.scalars, 3);   // fission
+    h->launch_count += 3;
     CUDA_TRY(cudaMemcpyAsync(h->d.scalars + 4, h->d.leakage, sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
     if (h->nranks > 1) {
         int rc = allreduce_scalars(h, h->d.scalars + 2, 3);   // solver.c:1394-1418, one vector
@@ -951,6 +999,9 @@ extern "C" float moc_get_leakage(moc_handle *h)
     cudaStreamSynchronize(h->stream);
     return v;
 }
+
+extern "C" void *moc_get_stream(moc_handle *h) { return h ? (void *)h->stream : nullptr; }
+extern "C" long moc_get_launch_count(moc_handle *h) { return h ? h->launch_count : -1; }
 
 extern "C" int moc_synchronize(moc_handle *h)
 {
@@ -1111,99 +1162,100 @@ static int allreduce_scalars(moc_handle *h, float *dev, int count)
     return MOC_OK;
 }
 
-// comms.c:12-28,75-83: tracks per face, in whole messages of 10000 tracks
-static void exchange_plan(const Input &I, long num_messages[6])
+// fast_transfer_boundary_fluxes (comms.c:5-196) on the device, driven by the host schedule
+// moc_exchange_plan() (moc_host.c).  Chunks sit at the head of the flux slab in (round,
+// direction) order.  Border faces: the chunk's pairwise sum goes to the leakage, zeros come
+// back.  Interior faces: ncclSend of the chunk to send_to, ncclRecv from recv_from into a
+// staging buffer (a chunk is sent and overwritten at the same offset, so it cannot be
+// received in place), scattered back over the same offsets after the group.
+// Three kernels + one NCCL group per call, whatever the number of chunks.
+static int exchange_on_stream(moc_handle *h, const CommGrid *grid, cudaStream_t st)
 {
-    const int tracks_per_msg = 10000;
-    const float hgt = I.domain_height;
-    const float x = I.assembly_width;
-    long per_axial = I.ntracks * x / (2 * x + 4 * hgt);
-    long per_radial = I.ntracks * hgt / (2 * x + 4 * hgt);
-    const long remaining = I.ntracks - 2 * per_axial - 4 * per_radial;
-    long add_radial = remaining * (4 * hgt / (2 * x + 4 * hgt));
-    add_radial = 4 * (add_radial / 4);
-    per_radial += add_radial / 4;
-    const long add_axial = remaining - add_radial;
-    per_axial += add_axial / 2;
-    for (int d = 0; d < 4; d++) num_messages[d] = per_radial / tracks_per_msg;
-    for (int d = 4; d < 6; d++) num_messages[d] = per_axial / tracks_per_msg;
-}
-
-// fast_transfer_boundary_fluxes (comms.c:5-196) on the device.  Chunks sit at the head of
-// the psi slab in (round, direction) order.  Border faces: the chunk's pairwise sum goes to
-// the leakage, zeros come back.  Interior faces: ncclSend of the chunk to *_dest, ncclRecv
-// from *_src into a staging buffer, copied back over the same offsets after the group.
-extern "C" int moc_exchange(moc_handle *h, const CommGrid *grid)
-{
-    if (!h || !grid) return MOC_EINVAL;
-    CUDA_TRY(cudaSetDevice(h->device));
-    long nmsg[6];
-    exchange_plan(h->I, nmsg);
-    const long long chunk = (long long)h->G * 10000;
-    long rounds = 0, total_chunks = 0;
-    for (int d = 0; d < 6; d++) {
-        rounds = std::max(rounds, nmsg[d]);
-        total_chunks += nmsg[d];
-    }
-    if (total_chunks * chunk > 2 * h->T3 * h->G) {
-        moc_set_error("exchange plan exceeds the flux slab");
+    const long n_ops = moc_exchange_plan(&h->I, grid, nullptr, 0);
+    if (n_ops < 0) return (int)n_ops;
+    if (n_ops == 0) return MOC_OK;
+    std::vector<moc_exchange_op> ops((size_t)n_ops);
+    moc_exchange_plan(&h->I, grid, ops.data(), n_ops);
+    const long long chunk = ops[0].count;
+    if (chunk % 4 != 0) {
+        moc_set_error("exchange chunk of %lld floats is not a multiple of 4", chunk);
         return MOC_EINVAL;
     }
-    if (total_chunks == 0) return MOC_OK;
-    const int dest[6] = {grid->x_pos_dest, grid->x_neg_dest, grid->y_pos_dest,
-                         grid->y_neg_dest, grid->z_pos_dest, grid->z_neg_dest};
-    const int from[6] = {grid->x_pos_src, grid->x_neg_src, grid->y_pos_src,
-                         grid->y_neg_src, grid->z_pos_src, grid->z_neg_src};
+    // device-side tables: [0,n) destination offsets (float4 units), [n,2n) staging offsets or -1,
+    // [2n, 2n+n_border) offsets (floats) of the chunks that leak
+    std::vector<long long> tab((size_t)3 * n_ops);
+    long n_border = 0, n_recv = 0;
     bool any_peer = false;
-    for (int d = 0; d < 6; d++) any_peer = any_peer || dest[d] != -1 || from[d] != -1;
+    for (long k = 0; k < n_ops; k++) {
+        tab[(size_t)k] = ops[(size_t)k].offset / 4;
+        if (ops[(size_t)k].recv_from >= 0) tab[(size_t)(n_ops + k)] = (n_recv++) * (chunk / 4);
+        else tab[(size_t)(n_ops + k)] = -1;
+        if (ops[(size_t)k].send_to < 0) tab[(size_t)(2 * n_ops + n_border++)] = ops[(size_t)k].offset;
+        any_peer = any_peer || ops[(size_t)k].send_to >= 0 || ops[(size_t)k].recv_from >= 0;
+    }
     if (any_peer && !h->nccl_comm) {
         moc_set_error("moc_exchange: neighbours present but moc_comm_init was not called");
         return MOC_ECOMM;
     }
-    if (any_peer && !h->recv_stage) {
-        CUDA_TRY(cudaMalloc((void **)&h->recv_stage, sizeof(float) * (size_t)total_chunks * chunk));
+    if (h->exch_capacity < n_ops) {
+        if (h->exch_table) cudaFree(h->exch_table);
+        if (h->exch_sums) cudaFree(h->exch_sums);
+        h->exch_table = nullptr;
+        h->exch_sums = nullptr;
+        CUDA_TRY(cudaMalloc((void **)&h->exch_table, sizeof(long long) * 3 * (size_t)n_ops));
+        CUDA_TRY(cudaMalloc((void **)&h->exch_sums, sizeof(float) * (size_t)n_ops));
+        h->exch_capacity = n_ops;
     }
-    // 1) leakage of border faces, in the reference's (round, direction) accumulation order
-    {
-        long long at = 0;
-        for (long i = 0; i < rounds; i++)
-            for (int d = 0; d < 6; d++) {
-                if (i >= nmsg[d]) continue;
-                if (dest[d] == -1)
-                    chunk_leakage_kernel<<<1, 256, 0, h->stream>>>(h->d.psi + at, chunk, h->d.leakage);
-                at += chunk;
-            }
+    if (n_recv > h->stage_chunks) {
+        if (h->recv_stage) cudaFree(h->recv_stage);
+        h->recv_stage = nullptr;
+        CUDA_TRY(cudaMalloc((void **)&h->recv_stage, sizeof(float) * (size_t)n_recv * (size_t)chunk));
+        h->stage_chunks = n_recv;
     }
-    // 2) all sends and receives of all rounds in one NCCL group (tag = direction is implied by
-    //    the per-peer FIFO order, which is the (round, direction) order on both sides)
+    // pageable source: the copy is staged by the runtime before the call returns
+    CUDA_TRY(cudaMemcpyAsync(h->exch_table, tab.data(), sizeof(long long) * 3 * (size_t)n_ops,
+                             cudaMemcpyHostToDevice, st));
+    // 1) leakage of the border faces, in the reference's accumulation order
+    if (n_border > 0) {
+        border_chunk_sums_kernel<<<(unsigned)n_border, 256, 0, st>>>(h->d.psi, h->exch_table + 2 * n_ops, chunk,
+                                                                    h->exch_sums);
+        leakage_accumulate_kernel<<<1, 1, 0, st>>>(h->exch_sums, (int)n_border, h->d.leakage);
+        h->launch_count += 2;
+    }
+    // 2) every send and receive of every round in one NCCL group.  The reference tags messages
+    //    with the direction; here the per-peer FIFO order -- (round, direction) on both sides --
+    //    pairs them up.
     if (any_peer) {
         NCCL_TRY(g_nccl.group_start());
-        long long at = 0;
-        for (long i = 0; i < rounds; i++)
-            for (int d = 0; d < 6; d++) {
-                if (i >= nmsg[d]) continue;
-                if (dest[d] != -1)
-                    NCCL_TRY(g_nccl.send(h->d.psi + at, (size_t)chunk, 7, dest[d], h->nccl_comm, h->stream));
-                if (from[d] != -1)
-                    NCCL_TRY(g_nccl.recv(h->recv_stage + at, (size_t)chunk, 7, from[d], h->nccl_comm, h->stream));
-                at += chunk;
-            }
+        long r = 0;
+        for (long k = 0; k < n_ops; k++) {
+            const moc_exchange_op &op = ops[(size_t)k];
+            if (op.send_to >= 0)
+                NCCL_TRY(g_nccl.send(h->d.psi + op.offset, (size_t)chunk, /*ncclFloat*/ 7, op.send_to, h->nccl_comm, st));
+            if (op.recv_from >= 0)
+                NCCL_TRY(g_nccl.recv(h->recv_stage + (size_t)(r++) * (size_t)chunk, (size_t)chunk, 7, op.recv_from,
+                                     h->nccl_comm, st));
+        }
         NCCL_TRY(g_nccl.group_end());
     }
     // 3) received chunks (or zeros) replace the sent ones
     {
-        long long at = 0;
-        for (long i = 0; i < rounds; i++)
-            for (int d = 0; d < 6; d++) {
-                if (i >= nmsg[d]) continue;
-                if (from[d] == -1)
-                    CUDA_TRY(cudaMemsetAsync(h->d.psi + at, 0, sizeof(float) * (size_t)chunk, h->stream));
-                else
-                    CUDA_TRY(cudaMemcpyAsync(h->d.psi + at, h->recv_stage + at, sizeof(float) * (size_t)chunk,
-                                             cudaMemcpyDeviceToDevice, h->stream));
-                at += chunk;
-            }
+        const dim3 grid3(16, (unsigned)n_ops);
+        exchange_scatter_kernel<<<grid3, 256, 0, st>>>(reinterpret_cast<float4 *>(h->d.psi),
+                                                      reinterpret_cast<const float4 *>(h->recv_stage), h->exch_table,
+                                                      h->exch_table + n_ops, chunk / 4);
+        h->launch_count++;
     }
+    CUDA_TRY(cudaGetLastError());
+    return MOC_OK;
+}
+
+extern "C" int moc_exchange(moc_handle *h, const CommGrid *grid)
+{
+    if (!h || !grid) return MOC_EINVAL;
+    CUDA_TRY(cudaSetDevice(h->device));
+    int rc = exchange_on_stream(h, grid, h->stream);
+    if (rc) return rc;
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     CUDA_TRY(cudaGetLastError());
     return MOC_OK;

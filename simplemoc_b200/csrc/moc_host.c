@@ -213,6 +213,59 @@ double moc_time_per_intersection(const Input *in, double seconds)
     return seconds / (double)in->segments_processed * 1.0e9 / (double)in->n_egroups;
 }
 
+/* ------------------------------------------------------------------ boundary exchange schedule */
+
+/* comms.c:12-28,75-83: tracks per face from the surface-area ratio, in whole messages of
+ * 10000 tracks; then the (round, direction) order of comms.c:100-183. */
+long moc_exchange_plan(const Input *in, const CommGrid *grid, moc_exchange_op *ops, long max_ops)
+{
+    const int tracks_per_msg = 10000;
+    const float hgt = in->domain_height;
+    const float x = in->assembly_width;
+    long per_axial = in->ntracks * x / (2 * x + 4 * hgt);
+    long per_radial = in->ntracks * hgt / (2 * x + 4 * hgt);
+    const long remaining = in->ntracks - 2 * per_axial - 4 * per_radial;
+    long add_radial = remaining * (4 * hgt / (2 * x + 4 * hgt));
+    add_radial = 4 * (add_radial / 4);
+    per_radial += add_radial / 4;
+    const long add_axial = remaining - add_radial;
+    per_axial += add_axial / 2;
+    long nmsg[6], rounds = 0, total = 0;
+    for (int d = 0; d < 4; d++) nmsg[d] = per_radial / tracks_per_msg;
+    for (int d = 4; d < 6; d++) nmsg[d] = per_axial / tracks_per_msg;
+    for (int d = 0; d < 6; d++) {
+        if (nmsg[d] > rounds) rounds = nmsg[d];
+        total += nmsg[d];
+    }
+    const long long chunk = (long long)in->n_egroups * tracks_per_msg;
+    if (total * chunk > 2ll * in->ntracks * in->n_egroups) {
+        moc_set_error("exchange plan (%ld messages of %lld floats) exceeds the flux slab", total, chunk);
+        return MOC_EINVAL;
+    }
+    if (!ops) return total;
+    const int dest[6] = { grid->x_pos_dest, grid->x_neg_dest, grid->y_pos_dest,
+                          grid->y_neg_dest, grid->z_pos_dest, grid->z_neg_dest };
+    const int from[6] = { grid->x_pos_src, grid->x_neg_src, grid->y_pos_src,
+                          grid->y_neg_src, grid->z_pos_src, grid->z_neg_src };
+    long k = 0;
+    long long at = 0;
+    for (long i = 0; i < rounds; i++)
+        for (int d = 0; d < 6; d++) {
+            if (i >= nmsg[d]) continue;
+            if (k < max_ops) {
+                ops[k].offset = at;
+                ops[k].count = chunk;
+                ops[k].round = (int)i;
+                ops[k].direction = d;
+                ops[k].send_to = dest[d];
+                ops[k].recv_from = from[d];
+            }
+            k++;
+            at += chunk;
+        }
+    return k;
+}
+
 /* ------------------------------------------------------------------ construction */
 
 /* utils.c:11-26 with explicit stream positions */

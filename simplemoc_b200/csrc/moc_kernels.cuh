@@ -27,6 +27,11 @@
 
 #include "moc_rng.h"
 
+// minimum resident CTAs per SM the attenuation kernel is compiled for (register budget)
+#ifndef MOC_ATT_MIN_BLOCKS
+#define MOC_ATT_MIN_BLOCKS 1
+#endif
+
 namespace moc {
 
 // ------------------------------------------------------------------ parameters
@@ -75,7 +80,7 @@ struct AttenuateParams {
     float *fine_flux;                 // [N][fai][G]
     const float *sigT;                // [N][G]
     const float *table;               // [2*table_n]
-    float table_dx, table_max, table_half_dx;
+    float table_dx, table_rdx, table_max, table_half_dx;
     int table_n;
     long long first_track, end_track; // tracks of this batch
     int P, Z, G, fai;
@@ -404,94 +409,167 @@ __global__ void pair_scan_kernel(const unsigned long long *in, unsigned long lon
 
 // ------------------------------------------------------------------ K1: attenuation
 
-// 1 - exp(-x).  TABLE: the reference's linear table, cell chosen exactly as
-// solver.c:1448 does (IEEE divide; the slope sign is the reference's).
-// SFU: MUFU.EX2 via __expf.  Both keep the reference's x > maxVal -> 1 rule.
-template <bool SFU>
-__device__ __forceinline__ float one_minus_exp(float x, const float2 *tab, float dx, float half_dx,
-                                               float x_max)
+// MUFU.RCP / MUFU.EX2 without the range fix-ups of the libdevice wrappers
+__device__ __forceinline__ float rcp_approx(float x)
 {
-    if (SFU) {
-        const float v = 1.0f - __expf(-x);
-        return x > x_max ? 1.0f : v;
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float ex2_approx(float x)
+{
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// The table cell the reference picks for x (solver.c:1448): (int)(x / dx + 0.5f * dx), with an
+// IEEE float division.  EXACT_DIV: the division instruction sequence of __fdiv_rn.
+// !EXACT_DIV: quotient by one Newton step on x * fl(1/dx) (3 instructions); the host only
+// selects this variant after table_cell_check_kernel has verified, for EVERY float in
+// [0, maxVal], that it lands in the same cell.
+template <bool EXACT_DIV>
+__device__ __forceinline__ int table_cell(float x, float dx, float rdx, float half_dx)
+{
+    float q;
+    if (EXACT_DIV) {
+        q = __fdiv_rn(x, dx);
     } else {
-        if (x > x_max) return 1.0f;
-        const int cell = (int)__fadd_rn(__fdiv_rn(x, dx), half_dx);
+        q = __fmul_rn(x, rdx);
+        const float rem = __fmaf_rn(-q, dx, x);
+        q = __fmaf_rn(rem, rdx, q);
+    }
+    return __float2int_rz(__fadd_rn(q, half_dx));
+}
+
+// exhaustive check of the fast cell selection: one thread per float bit pattern in [0, bits_max]
+__global__ void table_cell_check_kernel(unsigned int bits_max, float dx, float rdx, float half_dx,
+                                        unsigned long long *mismatches)
+{
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    unsigned int bad = 0;
+    for (unsigned long long b = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; b <= bits_max; b += stride) {
+        const float x = __uint_as_float((unsigned int)b);
+        bad += table_cell<true>(x, dx, rdx, half_dx) != table_cell<false>(x, dx, rdx, half_dx);
+    }
+    if (bad) atomicAdd(mismatches, (unsigned long long)bad);
+}
+
+struct TableConsts {
+    float dx, rdx, half_dx, x_max;
+    int n;   // cells; s_tab[n] = (0, 1): the value of every x > x_max
+};
+
+// E = 1 - exp(-x) and D = exp(-x) = 1 - E.
+//  MODE 0: the reference's linear table, cell chosen exactly as solver.c:1448 does (the slope sign
+//          is the reference's), IEEE division.
+//  MODE 1: the same with the verified fast division.
+//  MODE 2: SFU: MUFU.EX2.
+// All keep the reference's x > maxVal -> 1 rule (solver.c:1444-1445).
+template <int MODE>
+__device__ __forceinline__ void one_minus_exp(float x, const float2 *tab, const TableConsts &tc, float &E, float &D)
+{
+    if (MODE == 2) {
+        const float d = ex2_approx(x * -1.4426950408889634f);
+        const bool big = x > tc.x_max;
+        D = big ? 0.0f : d;
+        E = 1.0f - D;
+    } else {
+        int cell = table_cell<MODE == 0>(x, tc.dx, tc.rdx, tc.half_dx);
+        cell = x > tc.x_max ? tc.n : cell;
         const float2 line = tab[cell];
-        return fmaf(line.x, x, line.y);
+        E = fmaf(line.x, x, line.y);
+        D = 1.0f - E;
     }
 }
 
+// per-segment scalars of attenuate_fluxes, hoisted out of the group loop
 struct SegmentScalars {
-    float ds, zin, mu, mu2, weight;
+    float ds;
+    float a1, a2;      // zin/(2dz), zin^2/(2dz^2)          : q0 = y2 + a1 (y1-y3) + a2 (y1-2y2+y3)
+    float b1, b2;      // mu/(2dz), 2 mu zin/(2dz^2)        : q1 mu
+    float b3, b3_3;    // mu^2/(2dz^2), the same / 3         : q2 mu^2
+    float weight;
 };
 
 // one energy group of attenuate_fluxes (solver.c:66-82, 146-279).  Returns the tally.
-template <bool SFU>
+// Same formulas, regrouped so that every factor that does not depend on the group is a
+// per-segment scalar and every division is a multiplication by MUFU.RCP(sigT).
+template <int MODE>
 __device__ __forceinline__ float attenuate_quadratic(float y1, float y2, float y3, float sigT, float &psi,
-                                                     const SegmentScalars &sc, const AttenuateParams &a,
-                                                     const float2 *tab)
+                                                     const SegmentScalars &k, const float2 *tab,
+                                                     const TableConsts &tc)
 {
-    const float c1 = (y1 - y3) * a.inv_2dz;
-    const float c2 = (y1 - 2.f * y2 + y3) * a.inv_2dz2;
-    const float q0 = y2 + c1 * sc.zin + c2 * sc.zin * sc.zin;
-    const float q1 = c1 + 2.f * c2 * sc.zin;
-    const float q2 = c2;
-    const float tau = sigT * sc.ds;
-    const float ex = one_minus_exp<SFU>(tau, tab, a.table_dx, a.table_half_dx, a.table_max);
-    const float r1 = __frcp_rn(sigT);
+    const float d = y1 - y3;
+    const float e = fmaf(-2.f, y2, y1 + y3);
+    const float q0 = fmaf(k.a2, e, fmaf(k.a1, d, y2));
+    const float q1m = fmaf(k.b2, e, k.b1 * d);          // q1 * mu
+    const float q2m = k.b3 * e;                         // q2 * mu^2
+    const float q2m3 = k.b3_3 * e;                      // q2 * mu^2 / 3
+    const float tau = sigT * k.ds;
+    float E, D;
+    one_minus_exp<MODE>(tau, tab, tc, E, D);
+    const float r1 = rcp_approx(sigT);
     const float r2 = r1 * r1;
+    const float r3 = r2 * r1;
+    const float r4 = r2 * r2;
     // solver.c:175-176 exactly as parenthesised there
-    const float reuse = tau * (tau - 2.f) + 2.f * ex * (r1 * r2);
-    const float integral = (q0 * tau + (sigT * psi - q0) * ex) * r2 + q1 * sc.mu * reuse +
-                           q2 * sc.mu2 * (tau * (tau * (tau - 3.f) + 6.f) - 6.f * ex) *
-                               (r2 * r2 * (1.f / 3.f));
-    const float t1 = q0 * ex * r1;
-    const float t2 = q1 * sc.mu * (tau - ex) * r2;
-    const float t3 = q2 * sc.mu2 * reuse;
-    const float t4 = psi * (1.f - ex);
-    psi = t1 + t2 + t3 + t4;
-    return sc.weight * integral;
+    const float reuse = fmaf(2.f, E * r3, tau * (tau - 2.f));
+    float in = fmaf(q0, tau, fmaf(sigT, psi, -q0) * E) * r2;
+    in = fmaf(q1m, reuse, in);
+    const float cubic = fmaf(-6.f, E, tau * fmaf(tau, tau - 3.f, 6.f));
+    in = fmaf(q2m3, cubic * r4, in);
+    float out = (q0 * E) * r1;
+    out = fmaf(q1m * r2, tau - E, out);
+    out = fmaf(q2m, reuse, out);
+    psi = fmaf(psi, D, out);
+    return k.weight * in;
 }
 
 // one energy group of attenuate_FSR_fluxes (solver.c:1104-1115)
-template <bool SFU>
-__device__ __forceinline__ float attenuate_flat(float src, float sigT, float &psi, const SegmentScalars &sc,
-                                                const AttenuateParams &a, const float2 *tab)
+template <int MODE>
+__device__ __forceinline__ float attenuate_flat(float src, float sigT, float &psi, const SegmentScalars &k,
+                                                const float2 *tab, const TableConsts &tc)
 {
-    const float tau = sigT * sc.ds;
-    const float ex = one_minus_exp<SFU>(tau, tab, a.table_dx, a.table_half_dx, a.table_max);
-    const float q = src * __frcp_rn(sigT);
-    const float dpsi = (psi - q) * ex;
+    const float tau = sigT * k.ds;
+    float E, D;
+    one_minus_exp<MODE>(tau, tab, tc, E, D);
+    const float q = __fdiv_rn(src, sigT);   // flat source: the difference psi - q cancels, keep the division exact
+    const float dpsi = (psi - q) * E;
     psi -= dpsi;
-    return sc.weight * dpsi;
+    return k.weight * dpsi;
 }
 
+// fine_flux is only ever reduced into by this kernel (never read), so the reductions carry no
+// "memory" clobber: the compiler may hoist the next segment's loads above them.
 __device__ __forceinline__ void red_add_v4(float *addr, float4 v)
 {
     // sm_90+: one 16-byte reduction instead of four 4-byte ones
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y),
-                 "f"(v.z), "f"(v.w)
-                 : "memory");
+                 "f"(v.z), "f"(v.w));
 }
 __device__ __forceinline__ void red_add(float *addr, float v)
 {
-    asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
+    asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v));
 }
 
 // L lanes cooperate on one 3D track (32/L tracks per warp).  Lane `lit` of a track
 // owns NV4 float4 group-quads  g = 4*(lit + L*v) ..+3   and NS single groups
 // g = 4*L*NV4 + lit + L*s  (so G=104 -> L=8, NV4=3, NS=1 uses every lane fully).
 // The angular flux of the track lives in registers for the whole track.
-template <int L, int NV4, int NS, bool SFU, bool FLAT>
-__global__ void __launch_bounds__(128) attenuate_kernel(const AttenuateParams a)
+template <int L, int NV4, int NS, int MODE, bool FLAT>
+__global__ void __launch_bounds__(128, MOC_ATT_MIN_BLOCKS) attenuate_kernel(const AttenuateParams a)
 {
     extern __shared__ float2 s_tab[];
-    if (!SFU) {
+    if (MODE != 2) {
         for (int e = threadIdx.x; e < a.table_n; e += blockDim.x)
             s_tab[e] = make_float2(a.table[2 * e], a.table[2 * e + 1]);
+        if (threadIdx.x == 0) s_tab[a.table_n] = make_float2(0.f, 1.f);
         __syncthreads();
     }
+    TableConsts tc;
+    tc.dx = a.table_dx; tc.rdx = a.table_rdx; tc.half_dx = a.table_half_dx; tc.x_max = a.table_max;
+    tc.n = a.table_n;
     constexpr int TPW = 32 / L;
     const int lane = threadIdx.x & 31;
     const int lit = lane % L;
@@ -501,20 +579,23 @@ __global__ void __launch_bounds__(128) attenuate_kernel(const AttenuateParams a)
 
     uint32_t n_rec = 0, at = 0;
     SegmentScalars sc;
-    sc.mu = 0.f; sc.mu2 = 0.f; sc.weight = 0.f; sc.ds = 0.f; sc.zin = 0.f;
-    float w0 = 0.f;
+    sc.ds = 0.f; sc.a1 = sc.a2 = sc.b1 = sc.b2 = sc.b3 = sc.b3_3 = 0.f; sc.weight = 0.f;
+    float mu = 0.f;
     if (valid) {
         n_rec = a.seg_count[t];
         at = a.track_off[t - a.first_track];
         const long long pair = t / a.Z;
         const int j = (int)(pair % a.P);
         const long long i = pair / a.P;
-        sc.mu = a.mu[j];
-        sc.mu2 = sc.mu * sc.mu;
-        w0 = __fmul_rn(a.p_weight[t], a.az_weight[i]);       // solver.c:49
-        if (FLAT) w0 = __fmul_rn(w0, sc.mu);                 // solver.c:1064
+        mu = a.mu[j];
+        float w0 = __fmul_rn(a.p_weight[t], a.az_weight[i]);   // solver.c:49
+        if (FLAT) w0 = __fmul_rn(w0, mu);                      // solver.c:1064
         sc.weight = w0;
+        sc.b1 = mu * a.inv_2dz;
+        sc.b3 = mu * mu * a.inv_2dz2;
+        sc.b3_3 = sc.b3 * (1.f / 3.f);
     }
+    const float two_mu_c = 2.f * mu * a.inv_2dz2;
     unsigned int longest = n_rec;
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {
@@ -538,11 +619,31 @@ __global__ void __launch_bounds__(128) attenuate_kernel(const AttenuateParams a)
         psi1[s] = (valid && g < G) ? psi_row[g] : 0.f;
     }
 
+    // the record of the next segment is fetched one iteration ahead
+    const float *rec_ds = a.rec_ds + at;
+    const float *rec_zin = a.rec_zin + at;
+    const uint32_t *rec_code = a.rec_code + at;
+    float next_ds = 0.f, next_zin = 0.f;
+    uint32_t next_code = 0;
+    if (n_rec > 0) {
+        next_ds = __ldg(rec_ds);
+        next_zin = __ldg(rec_zin);
+        next_code = __ldg(rec_code);
+    }
+
     for (unsigned int sgm = 0; sgm < longest; sgm++) {
         if (sgm < n_rec) {
-            sc.ds = a.rec_ds[at + sgm];
-            sc.zin = a.rec_zin[at + sgm];
-            const uint32_t code = a.rec_code[at + sgm];
+            sc.ds = next_ds;
+            const float zin = next_zin;
+            const uint32_t code = next_code;
+            if (sgm + 1 < n_rec) {
+                next_ds = __ldg(rec_ds + sgm + 1);
+                next_zin = __ldg(rec_zin + sgm + 1);
+                next_code = __ldg(rec_code + sgm + 1);
+            }
+            sc.a1 = zin * a.inv_2dz;
+            sc.a2 = zin * zin * a.inv_2dz2;
+            sc.b2 = two_mu_c * zin;
             const uint32_t qsr = code & 0xffffffu;
             const uint32_t r0 = (code >> 24) & 63u;
             const uint32_t which = code >> 30;
@@ -558,18 +659,18 @@ __global__ void __launch_bounds__(128) attenuate_kernel(const AttenuateParams a)
                     float4 tally;
                     if (FLAT) {
                         const float4 y = __ldg(reinterpret_cast<const float4 *>(ya + g));
-                        tally.x = attenuate_flat<SFU>(y.x, s4.x, psi4[v].x, sc, a, s_tab);
-                        tally.y = attenuate_flat<SFU>(y.y, s4.y, psi4[v].y, sc, a, s_tab);
-                        tally.z = attenuate_flat<SFU>(y.z, s4.z, psi4[v].z, sc, a, s_tab);
-                        tally.w = attenuate_flat<SFU>(y.w, s4.w, psi4[v].w, sc, a, s_tab);
+                        tally.x = attenuate_flat<MODE>(y.x, s4.x, psi4[v].x, sc, s_tab, tc);
+                        tally.y = attenuate_flat<MODE>(y.y, s4.y, psi4[v].y, sc, s_tab, tc);
+                        tally.z = attenuate_flat<MODE>(y.z, s4.z, psi4[v].z, sc, s_tab, tc);
+                        tally.w = attenuate_flat<MODE>(y.w, s4.w, psi4[v].w, sc, s_tab, tc);
                     } else {
                         const float4 y1 = __ldg(reinterpret_cast<const float4 *>(ya + g));
                         const float4 y2 = __ldg(reinterpret_cast<const float4 *>(ya + G + g));
                         const float4 y3 = __ldg(reinterpret_cast<const float4 *>(ya + 2 * G + g));
-                        tally.x = attenuate_quadratic<SFU>(y1.x, y2.x, y3.x, s4.x, psi4[v].x, sc, a, s_tab);
-                        tally.y = attenuate_quadratic<SFU>(y1.y, y2.y, y3.y, s4.y, psi4[v].y, sc, a, s_tab);
-                        tally.z = attenuate_quadratic<SFU>(y1.z, y2.z, y3.z, s4.z, psi4[v].z, sc, a, s_tab);
-                        tally.w = attenuate_quadratic<SFU>(y1.w, y2.w, y3.w, s4.w, psi4[v].w, sc, a, s_tab);
+                        tally.x = attenuate_quadratic<MODE>(y1.x, y2.x, y3.x, s4.x, psi4[v].x, sc, s_tab, tc);
+                        tally.y = attenuate_quadratic<MODE>(y1.y, y2.y, y3.y, s4.y, psi4[v].y, sc, s_tab, tc);
+                        tally.z = attenuate_quadratic<MODE>(y1.z, y2.z, y3.z, s4.z, psi4[v].z, sc, s_tab, tc);
+                        tally.w = attenuate_quadratic<MODE>(y1.w, y2.w, y3.w, s4.w, psi4[v].w, sc, s_tab, tc);
                     }
                     red_add_v4(fl + g, tally);
                 }
@@ -581,10 +682,10 @@ __global__ void __launch_bounds__(128) attenuate_kernel(const AttenuateParams a)
                     const float s1 = __ldg(st + g);
                     float tally;
                     if (FLAT) {
-                        tally = attenuate_flat<SFU>(__ldg(ya + g), s1, psi1[s], sc, a, s_tab);
+                        tally = attenuate_flat<MODE>(__ldg(ya + g), s1, psi1[s], sc, s_tab, tc);
                     } else {
-                        tally = attenuate_quadratic<SFU>(__ldg(ya + g), __ldg(ya + G + g), __ldg(ya + 2 * G + g),
-                                                         s1, psi1[s], sc, a, s_tab);
+                        tally = attenuate_quadratic<MODE>(__ldg(ya + g), __ldg(ya + G + g), __ldg(ya + 2 * G + g),
+                                                          s1, psi1[s], sc, s_tab, tc);
                     }
                     red_add(fl + g, tally);
                 }
@@ -823,12 +924,41 @@ __global__ void patch_tracks_kernel(TrackImage *img, long long n, const float *z
     img[t].z_height = z_height[t];
 }
 
-// pairwise_sum of a chunk of the psi slab per CTA launch (border-face leakage, comms.c:120-121)
-__global__ void chunk_leakage_kernel(const float *chunk, long long n, float *leakage)
+// ------------------------------------------------------------------ K5: boundary exchange helpers
+
+// sums[b] = pairwise_sum(slab[offsets[b] .. +n))  -- one CTA of 256 threads per border chunk
+// (comms.c:120-121: the flux leaving through a face without a neighbour)
+__global__ void border_chunk_sums_kernel(const float *slab, const long long *offsets, long long n, float *sums)
 {
     __shared__ float slots[256];
-    const float s = pairwise_sum_cta(chunk, n, slots);
-    if (threadIdx.x == 0) *leakage = __fadd_rn(*leakage, s);
+    const float s = pairwise_sum_cta(slab + offsets[blockIdx.x], n, slots);
+    if (threadIdx.x == 0) sums[blockIdx.x] = s;
+}
+
+// *leakage += sums[0], then sums[1], ...: the reference adds the chunk sums one by one in
+// (round, direction) order (comms.c:118-121)  -- <<<1, 1>>>
+__global__ void leakage_accumulate_kernel(const float *sums, int n, float *leakage)
+{
+    float l = *leakage;
+    for (int b = 0; b < n; b++) l = __fadd_rn(l, sums[b]);
+    *leakage = l;
+}
+
+// chunk blockIdx.y of the plan: slab[dst[y] .. +n4 float4) = stage[src[y] ..] or zeros when
+// src[y] < 0 (comms.c:146-149,179-181).  n4 = chunk length in float4.
+__global__ void exchange_scatter_kernel(float4 *slab, const float4 *stage, const long long *dst,
+                                        const long long *src, long long n4)
+{
+    float4 *out = slab + dst[blockIdx.y];
+    const long long from = src[blockIdx.y];
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    if (from < 0) {
+        const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n4; e += stride) out[e] = zero;
+    } else {
+        const float4 *in = stage + from;
+        for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n4; e += stride) out[e] = in[e];
+    }
 }
 
 }  // namespace moc
