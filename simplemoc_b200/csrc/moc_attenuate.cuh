@@ -1,0 +1,373 @@
+/* moc_attenuate.cuh -- K1, the multigroup attenuation + scalar-flux tally kernel
+ * (reference src/solver.c:14-280 attenuate_fluxes, 1040-1138 attenuate_FSR_fluxes,
+ * 1441-1464 interpolateTable).  Included by moc_kernels.cuh inside namespace moc.
+ *
+ * Blackwell specifics
+ *   - the per-group arithmetic runs on PACKED FP32 pairs (FFMA2 / FMUL2 / FADD2, sm_100+):
+ *     one issue slot per two energy groups, which turns the kernel from issue-bound into
+ *     FMA-pipe/L2-bound (profiles/, DESIGN.md "K1");
+ *   - every division is a multiplication by MUFU.RCP(sigT); the exponential is either the
+ *     reference's table (shared memory, cell index bit-exact) or MUFU.EX2;
+ *   - the gathered source rows (3 x G floats + sigT) are 128-byte-per-8-lanes float4 loads that
+ *     hit in the 126 MB L2 (the whole source slab is L2-resident); tallies leave as 16-byte
+ *     vector reductions (red.global.add.v4.f32).
+ */
+#pragma once
+
+// MUFU.RCP / MUFU.EX2 without the range fix-ups of the libdevice wrappers
+__device__ __forceinline__ float rcp_approx(float x)
+{
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float ex2_approx(float x)
+{
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// packed FP32x2 helpers (scalar operands broadcast for free: FFMA2 takes .F32 sources)
+__device__ __forceinline__ float2 bc(float v) { return make_float2(v, v); }
+__device__ __forceinline__ float2 neg2(float2 a) { return make_float2(-a.x, -a.y); }
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) { return __fadd2_rn(a, neg2(b)); }
+
+// The table cell the reference picks for x (solver.c:1448): (int)(x / dx + 0.5f * dx), with an
+// IEEE float division.  EXACT_DIV: the division instruction sequence of __fdiv_rn.
+// !EXACT_DIV: quotient by one Newton step on x * fl(1/dx) (3 instructions); the host only
+// selects this variant after table_cell_check_kernel has verified, for EVERY float in
+// [0, maxVal], that it lands in the same cell.
+template <bool EXACT_DIV>
+__device__ __forceinline__ int table_cell(float x, float dx, float rdx, float half_dx)
+{
+    float q;
+    if (EXACT_DIV) {
+        q = __fdiv_rn(x, dx);
+    } else {
+        q = __fmul_rn(x, rdx);
+        const float rem = __fmaf_rn(-q, dx, x);
+        q = __fmaf_rn(rem, rdx, q);
+    }
+    return __float2int_rz(__fadd_rn(q, half_dx));
+}
+
+// exhaustive check of the fast cell selection: every float bit pattern in [0, bits_max]
+__global__ void table_cell_check_kernel(unsigned int bits_max, float dx, float rdx, float half_dx,
+                                        unsigned long long *mismatches)
+{
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    unsigned int bad = 0;
+    for (unsigned long long b = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; b <= bits_max; b += stride) {
+        const float x = __uint_as_float((unsigned int)b);
+        bad += table_cell<true>(x, dx, rdx, half_dx) != table_cell<false>(x, dx, rdx, half_dx);
+    }
+    if (bad) atomicAdd(mismatches, (unsigned long long)bad);
+}
+
+struct TableConsts {
+    float dx, rdx, half_dx, x_max;
+    int n;                 // cells; entry n of the shared table is (slope 0, intercept 1): every x > x_max
+    const float *tab;      // shared memory, [n + 1] x (slope, intercept)
+};
+
+// per-segment scalars of attenuate_fluxes, hoisted out of the group loop
+struct SegmentScalars {
+    float ds;
+    float a1, a2;      // zin/(2dz), zin^2/(2dz^2)          : q0 = y2 + a1 (y1-y3) + a2 (y1-2y2+y3)
+    float b1, b2;      // mu/(2dz), 2 mu zin/(2dz^2)        : q1 mu
+    float b3;          // mu^2/(2dz^2)                       : q2 mu^2
+    float weight;
+};
+
+// E = 1 - exp(-x), D = exp(-x) = 1 - E for a PAIR of groups.
+//  MODE 0: the reference's linear table, cell chosen exactly as solver.c:1448 does (the slope sign
+//          is the reference's), IEEE division.
+//  MODE 1: the same with the verified fast division.
+//  MODE 2: SFU: MUFU.EX2.
+// All keep the reference's x > maxVal -> 1 rule (solver.c:1444-1445).  HI = false: only .x is live.
+template <int MODE, bool HI>
+__device__ __forceinline__ void one_minus_exp2(float2 x, const TableConsts &tc, float2 &E, float2 &D)
+{
+    if (MODE == 2) {
+        const float2 arg = mul2(x, bc(-1.4426950408889634f));
+        D.x = x.x > tc.x_max ? 0.0f : ex2_approx(arg.x);
+        D.y = HI ? (x.y > tc.x_max ? 0.0f : ex2_approx(arg.y)) : 0.0f;
+        E = sub2(bc(1.0f), D);
+    } else {
+        float2 t;
+        if (MODE == 0) {
+            t.x = __fadd_rn(__fdiv_rn(x.x, tc.dx), tc.half_dx);
+            t.y = HI ? __fadd_rn(__fdiv_rn(x.y, tc.dx), tc.half_dx) : 0.0f;
+        } else {
+            float2 q = mul2(x, bc(tc.rdx));
+            const float2 rem = fma2(neg2(q), bc(tc.dx), x);
+            q = fma2(rem, bc(tc.rdx), q);
+            t = add2(q, bc(tc.half_dx));
+        }
+        int c0 = __float2int_rz(t.x);
+        c0 = x.x > tc.x_max ? tc.n : c0;
+        float2 slope, icpt;
+        slope.x = tc.tab[2 * c0];          // two LDS.32 off one address: the halves of a packed
+        icpt.x = tc.tab[2 * c0 + 1];       // operand come from different cells, so no LDS.64
+        if (HI) {
+            int c1 = __float2int_rz(t.y);
+            c1 = x.y > tc.x_max ? tc.n : c1;
+            slope.y = tc.tab[2 * c1];
+            icpt.y = tc.tab[2 * c1 + 1];
+        } else {
+            slope.y = 0.0f;
+            icpt.y = 0.0f;
+        }
+        E = fma2(slope, x, icpt);
+        D = sub2(bc(1.0f), E);
+    }
+}
+
+// Two energy groups of attenuate_fluxes (solver.c:66-82, 146-279) on packed FP32 pairs.
+// Returns the two tallies.  Same formulas as the reference, regrouped so that every factor that
+// does not depend on the group is a per-segment scalar and every division is a multiplication by
+// MUFU.RCP(sigT):
+//   in  = [ q0 tau + (sigT psi - q0) E + q2 mu^2 C3 / sigT^2 ] / sigT^2 + q1 mu R
+//   out = q0 E / sigT + q1 mu (tau - E) / sigT^2 + q2 mu^2 R + psi (1 - E)
+//   R   = tau (tau - 2) + 2 E / sigT^3          (solver.c:175-176 as parenthesised there)
+//   C3  = [tau (tau (tau - 3) + 6) - 6 E] / 3
+template <int MODE, bool HI>
+__device__ __forceinline__ float2 attenuate_pair(float2 y1, float2 y2, float2 y3, float2 sigT, float2 &psi,
+                                                 const SegmentScalars &k, const TableConsts &tc)
+{
+    const float2 d = sub2(y1, y3);
+    const float2 e = fma2(bc(-2.f), y2, add2(y1, y3));
+    const float2 q0 = fma2(bc(k.a2), e, fma2(bc(k.a1), d, y2));
+    const float2 q1m = fma2(bc(k.b2), e, mul2(bc(k.b1), d));   // q1 * mu
+    const float2 q2m = mul2(bc(k.b3), e);                      // q2 * mu^2
+    const float2 tau = mul2(sigT, bc(k.ds));
+    float2 E, D;
+    one_minus_exp2<MODE, HI>(tau, tc, E, D);
+    float2 r1;
+    r1.x = rcp_approx(sigT.x);
+    r1.y = HI ? rcp_approx(sigT.y) : 0.0f;
+    const float2 r2 = mul2(r1, r1);
+    const float2 Er1 = mul2(E, r1);
+    const float2 reuse = fma2(bc(2.f), mul2(Er1, r2), mul2(tau, add2(tau, bc(-2.f))));
+    const float2 A = fma2(q0, tau, mul2(fma2(sigT, psi, neg2(q0)), E));
+    const float2 c3 = fma2(bc(-2.f), E, mul2(tau, fma2(tau, fma2(tau, bc(1.f / 3.f), bc(-1.f)), bc(2.f))));
+    const float2 X = fma2(mul2(q2m, r2), c3, A);
+    const float2 in = fma2(X, r2, mul2(q1m, reuse));
+    float2 out = mul2(q0, Er1);
+    out = fma2(mul2(q1m, r2), sub2(tau, E), out);
+    out = fma2(q2m, reuse, out);
+    psi = fma2(psi, D, out);
+    return mul2(bc(k.weight), in);
+}
+
+// one energy group of attenuate_FSR_fluxes (solver.c:1104-1115); scalar: 11 FLOP, not worth packing
+template <int MODE>
+__device__ __forceinline__ float attenuate_flat(float src, float sigT, float &psi, const SegmentScalars &k,
+                                                const TableConsts &tc)
+{
+    const float tau = sigT * k.ds;
+    float2 E, D;
+    one_minus_exp2<MODE, false>(make_float2(tau, 0.f), tc, E, D);
+    const float q = __fdiv_rn(src, sigT);   // flat source: the difference psi - q cancels, keep the division exact
+    const float dpsi = (psi - q) * E.x;
+    psi -= dpsi;
+    return k.weight * dpsi;
+}
+
+// fine_flux is only ever reduced into by this kernel (never read), so the reductions carry no
+// "memory" clobber: the compiler may hoist the next segment's loads above them.
+__device__ __forceinline__ void red_add_v4(float *addr, float4 v)
+{
+    // sm_90+: one 16-byte reduction instead of four 4-byte ones
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y),
+                 "f"(v.z), "f"(v.w));
+}
+__device__ __forceinline__ void red_add(float *addr, float v)
+{
+    asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v));
+}
+
+// L lanes cooperate on one 3D track (32/L tracks per warp).  Lane `lit` of a track
+// owns NV4 float4 group-quads  g = 4*(lit + L*v) ..+3   and NS single groups
+// g = 4*L*NV4 + lit + L*s  (so G=104 -> L=8, NV4=3, NS=1 uses every lane fully).
+// The angular flux of the track lives in registers for the whole track.
+// GC: the number of groups as a compile-time constant (row strides become immediates), 0 = a.G.
+template <int L, int NV4, int NS, int MODE, bool FLAT, int GC>
+__global__ void __launch_bounds__(128, MOC_ATT_MIN_BLOCKS) attenuate_kernel(const AttenuateParams a)
+{
+    extern __shared__ float s_tab[];   // [n+1] x (slope, intercept)
+    TableConsts tc;
+    tc.dx = a.table_dx; tc.rdx = a.table_rdx; tc.half_dx = a.table_half_dx; tc.x_max = a.table_max;
+    tc.n = a.table_n;
+    tc.tab = s_tab;
+    if (MODE != 2) {
+        for (int e = threadIdx.x; e < 2 * a.table_n; e += blockDim.x) s_tab[e] = a.table[e];
+        if (threadIdx.x == 0) {
+            s_tab[2 * a.table_n] = 0.f;
+            s_tab[2 * a.table_n + 1] = 1.f;
+        }
+        __syncthreads();
+    }
+    constexpr int TPW = 32 / L;
+    const int lane = threadIdx.x & 31;
+    const int lit = lane % L;
+    const int G = GC ? GC : a.G;
+    const int W = GC ? (GC + 31) / 32 * 32 : a.pitch;   // row pitch of the source slab: 128-byte aligned rows
+    const long long t = a.first_track + ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * TPW + lane / L;
+    const bool valid = t < a.end_track;
+
+    uint32_t n_rec = 0, at = 0;
+    SegmentScalars sc;
+    sc.ds = 0.f; sc.a1 = sc.a2 = sc.b1 = sc.b2 = sc.b3 = 0.f; sc.weight = 0.f;
+    float mu = 0.f;
+    if (valid) {
+        n_rec = a.seg_count[t];
+        at = a.track_off[t - a.first_track];
+        const long long pair = t / a.Z;
+        const int j = (int)(pair % a.P);
+        const long long i = pair / a.P;
+        mu = a.mu[j];
+        float w0 = __fmul_rn(a.p_weight[t], a.az_weight[i]);   // solver.c:49
+        if (FLAT) w0 = __fmul_rn(w0, mu);                      // solver.c:1064
+        sc.weight = w0;
+        sc.b1 = mu * a.inv_2dz;
+        sc.b3 = mu * mu * a.inv_2dz2;
+    }
+    const float two_mu_c = 2.f * mu * a.inv_2dz2;
+    unsigned int longest = n_rec;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        unsigned int o = __shfl_xor_sync(0xffffffffu, longest, d);
+        longest = o > longest ? o : longest;
+    }
+
+    // group ownership: quads at element offset 4*lit + 4*L*v, singles at g_tail + lit + L*s
+    constexpr int g_tail = 4 * L * NV4;
+    float4 psi4[NV4 > 0 ? NV4 : 1];
+    float psi1[NS > 0 ? NS : 1];
+    float *psi_row = a.psi + (size_t)2 * (size_t)(valid ? t : 0) * G;
+#pragma unroll
+    for (int v = 0; v < NV4; v++) {
+        const int g = 4 * (lit + L * v);
+        psi4[v] = (valid && g < G) ? *reinterpret_cast<const float4 *>(psi_row + g) : make_float4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int s = 0; s < NS; s++) {
+        const int g = g_tail + lit + L * s;
+        psi1[s] = (valid && g < G) ? psi_row[g] : 0.f;
+    }
+
+    // Segment records: the L lanes of a track fetch L consecutive records with one coalesced load
+    // (lane `lit` holds record block*L + lit) one block ahead of use; each segment's record is then
+    // broadcast from its holder with a width-L shuffle.
+    const float *rec_ds = a.rec_ds + at;
+    const float *rec_zin = a.rec_zin + at;
+    const uint32_t *rec_code = a.rec_code + at;
+    float cur_ds = 0.f, cur_zin = 0.f, nxt_ds = 0.f, nxt_zin = 0.f;
+    uint32_t cur_code = 0, nxt_code = 0;
+    if ((uint32_t)lit < n_rec) {
+        nxt_ds = __ldg(rec_ds + lit);
+        nxt_zin = __ldg(rec_zin + lit);
+        nxt_code = __ldg(rec_code + lit);
+    }
+    const float *const src_q = a.fine_source + 4 * lit;          // this lane's quads
+    const float *const sig_q = a.sigT + 4 * lit;
+    float *const flx_q = a.fine_flux + 4 * lit;
+    const float *const src_s = a.fine_source + g_tail + lit;     // this lane's single groups
+    const float *const sig_s = a.sigT + g_tail + lit;
+    float *const flx_s = a.fine_flux + g_tail + lit;
+
+    for (unsigned int sgm = 0; sgm < longest; sgm++) {
+        const int slot = sgm % L;
+        if (slot == 0) {
+            cur_ds = nxt_ds; cur_zin = nxt_zin; cur_code = nxt_code;
+            const uint32_t ahead = sgm + L + lit;
+            if (ahead < n_rec) {
+                nxt_ds = __ldg(rec_ds + ahead);
+                nxt_zin = __ldg(rec_zin + ahead);
+                nxt_code = __ldg(rec_code + ahead);
+            }
+        }
+        const float seg_ds = __shfl_sync(0xffffffffu, cur_ds, slot, L);
+        const float zin = __shfl_sync(0xffffffffu, cur_zin, slot, L);
+        const uint32_t code = __shfl_sync(0xffffffffu, cur_code, slot, L);
+        if (sgm < n_rec) {
+            sc.ds = seg_ds;
+            sc.a1 = zin * a.inv_2dz;
+            sc.a2 = zin * zin * a.inv_2dz2;
+            sc.b2 = two_mu_c * zin;
+            const uint32_t qsr = code & 0xffffffu;
+            const uint32_t r0 = (code >> 24) & 63u;
+            const uint32_t which = code >> 30;
+            // element offsets inside the source slab (< 2^32, checked by moc_create)
+            const uint32_t o_src = (qsr * a.fai + r0) * (uint32_t)W;
+            const uint32_t o_sig = qsr * (uint32_t)W;
+            const uint32_t o_flx = o_src + which * (uint32_t)W;
+#pragma unroll
+            for (int v = 0; v < NV4; v++) {
+                const int g = 4 * (lit + L * v);
+                if (g < G) {
+                    const float4 s4 = __ldg(reinterpret_cast<const float4 *>(sig_q + o_sig + 4 * L * v));
+                    float4 tally;
+                    if (FLAT) {
+                        const float4 y = __ldg(reinterpret_cast<const float4 *>(src_q + o_src + 4 * L * v));
+                        tally.x = attenuate_flat<MODE>(y.x, s4.x, psi4[v].x, sc, tc);
+                        tally.y = attenuate_flat<MODE>(y.y, s4.y, psi4[v].y, sc, tc);
+                        tally.z = attenuate_flat<MODE>(y.z, s4.z, psi4[v].z, sc, tc);
+                        tally.w = attenuate_flat<MODE>(y.w, s4.w, psi4[v].w, sc, tc);
+                    } else {
+                        const float4 y1 = __ldg(reinterpret_cast<const float4 *>(src_q + o_src + 4 * L * v));
+                        const float4 y2 = __ldg(reinterpret_cast<const float4 *>(src_q + o_src + W + 4 * L * v));
+                        const float4 y3 = __ldg(reinterpret_cast<const float4 *>(src_q + o_src + 2 * W + 4 * L * v));
+                        float2 plo = make_float2(psi4[v].x, psi4[v].y), phi = make_float2(psi4[v].z, psi4[v].w);
+                        const float2 tlo = attenuate_pair<MODE, true>(make_float2(y1.x, y1.y), make_float2(y2.x, y2.y),
+                                                                      make_float2(y3.x, y3.y), make_float2(s4.x, s4.y),
+                                                                      plo, sc, tc);
+                        const float2 thi = attenuate_pair<MODE, true>(make_float2(y1.z, y1.w), make_float2(y2.z, y2.w),
+                                                                      make_float2(y3.z, y3.w), make_float2(s4.z, s4.w),
+                                                                      phi, sc, tc);
+                        psi4[v] = make_float4(plo.x, plo.y, phi.x, phi.y);
+                        tally = make_float4(tlo.x, tlo.y, thi.x, thi.y);
+                    }
+                    red_add_v4(flx_q + o_flx + 4 * L * v, tally);
+                }
+            }
+#pragma unroll
+            for (int s = 0; s < NS; s++) {
+                const int g = g_tail + lit + L * s;
+                if (g < G) {
+                    const float s1 = __ldg(sig_s + o_sig + L * s);
+                    float tally;
+                    if (FLAT) {
+                        tally = attenuate_flat<MODE>(__ldg(src_s + o_src + L * s), s1, psi1[s], sc, tc);
+                    } else {
+                        float2 p = make_float2(psi1[s], 0.f);
+                        const float2 tl = attenuate_pair<MODE, false>(
+                            make_float2(__ldg(src_s + o_src + L * s), 0.f), make_float2(__ldg(src_s + o_src + W + L * s), 0.f),
+                            make_float2(__ldg(src_s + o_src + 2 * W + L * s), 0.f), make_float2(s1, 0.f), p, sc, tc);
+                        psi1[s] = p.x;
+                        tally = tl.x;
+                    }
+                    red_add(flx_s + o_flx + L * s, tally);
+                }
+            }
+        }
+    }
+
+    if (valid) {
+#pragma unroll
+        for (int v = 0; v < NV4; v++) {
+            const int g = 4 * (lit + L * v);
+            if (g < G) *reinterpret_cast<float4 *>(psi_row + g) = psi4[v];
+        }
+#pragma unroll
+        for (int s = 0; s < NS; s++) {
+            const int g = g_tail + lit + L * s;
+            if (g < G) psi_row[g] = psi1[s];
+        }
+    }
+}

@@ -120,6 +120,7 @@ struct moc_handle {
     Input I;
     long long T2 = 0, T3 = 0, N = 0, X = 0, S2 = 0;
     int P = 0, Z = 0, G = 0, F = 0;
+    int Gp = 0;                    // device row pitch of the source slab: G rounded up to 32 floats (128 B)
     Table table_host;              // values pointer owned by the caller's Params; copied
     float table_dx = 0, table_max = 0;
     int table_n = 0;
@@ -183,6 +184,21 @@ static void free_buffers(DeviceBuffers &d)
     for (void *p : all)
         if (p) cudaFree(p);
     d = DeviceBuffers();
+}
+
+
+// The source slab on the device keeps the reference's order (fine_source | fine_flux | sigT,
+// source.c:121-152) but pads every row of G floats to Gp so that rows start on 128-byte lines.
+// rows [row0, row0 + rows) of the slab <-> a dense host array of G-float rows.
+static cudaError_t slab_to_device(moc_handle *h, size_t row0, size_t rows, const float *host)
+{
+    return cudaMemcpy2DAsync(h->d.src + row0 * h->Gp, sizeof(float) * h->Gp, host, sizeof(float) * h->G,
+                             sizeof(float) * h->G, rows, cudaMemcpyHostToDevice, h->stream);
+}
+static cudaError_t slab_to_host(moc_handle *h, size_t row0, size_t rows, float *host)
+{
+    return cudaMemcpy2DAsync(host, sizeof(float) * h->G, h->d.src + row0 * h->Gp, sizeof(float) * h->Gp,
+                             sizeof(float) * h->G, rows, cudaMemcpyDeviceToHost, h->stream);
 }
 
 // ------------------------------------------------------------------ host layout checks
@@ -358,8 +374,7 @@ static int upload_mutable(moc_handle *h, const HostLayout &L, bool with_backward
         CUDA_TRY(cudaMemcpy2DAsync(h->d.psi, sizeof(float) * 2 * G, L.psi, sizeof(float) * 2 * G,
                                    sizeof(float) * G, T3, cudaMemcpyHostToDevice, h->stream));
     }
-    CUDA_TRY(cudaMemcpyAsync(h->d.src, L.src, sizeof(float) * (size_t)(2 * h->F + 1) * (size_t)h->N * G,
-                             cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(slab_to_device(h, 0, (size_t)(2 * h->F + 1) * (size_t)h->N, L.src));
     CUDA_TRY(cudaGetLastError());
     return MOC_OK;
 }
@@ -401,6 +416,10 @@ static int create_common(const Input *I, const Params *P, int device, int source
                       I->fai, I->n_source_regions_per_node, I->z_stacked);
         return MOC_EINVAL;
     }
+    if ((double)(2 * I->fai + 1) * (double)I->n_source_regions_per_node * (double)((I->n_egroups + 31) / 32 * 32) >= 4294967296.0) {
+        moc_set_error("source slab has more than 2^32 elements (the attenuation kernel indexes it with 32 bits)");
+        return MOC_EINVAL;
+    }
     if ((rc = inspect_layout(I, P, source_stride, L))) return rc;
     CUDA_TRY(cudaSetDevice(device));
     moc_handle *h = new moc_handle();
@@ -413,6 +432,7 @@ static int create_common(const Input *I, const Params *P, int device, int source
     h->P = I->n_polar_angles;
     h->Z = I->z_stacked;
     h->G = I->n_egroups;
+    h->Gp = (I->n_egroups + 31) / 32 * 32;
     h->F = I->fai;
     h->source_stride = source_stride;
     memset(&h->timing, 0, sizeof h->timing);
@@ -436,7 +456,8 @@ static int create_common(const Input *I, const Params *P, int device, int source
     if ((rc = dev_alloc(&h->d.p_weight, T3))) return fail(rc);
     if ((rc = dev_alloc(&h->d.z_height, T3))) return fail(rc);
     if ((rc = dev_alloc(&h->d.psi, 2 * T3 * G))) return fail(rc);
-    if ((rc = dev_alloc(&h->d.src, (2 * F + 1) * N * G))) return fail(rc);
+    if ((rc = dev_alloc(&h->d.src, (2 * F + 1) * N * (size_t)h->Gp))) return fail(rc);
+    cudaMemsetAsync(h->d.src, 0, sizeof(float) * (2 * F + 1) * N * (size_t)h->Gp, h->stream);   // padding columns stay 0
     if ((rc = dev_alloc(&h->d.seg_count, T3))) return fail(rc);
     if ((rc = dev_alloc(&h->d.pair_count, pairs))) return fail(rc);
     if ((rc = dev_alloc(&h->d.pair_base, pairs + 1))) return fail(rc);
@@ -613,14 +634,14 @@ static LaneMap choose_lanes(int G, int lanes_override)
     return {L, 0, r};
 }
 
-template <int L, int NV4, int NS>
+template <int L, int NV4, int NS, int GC>
 static int launch_attenuate_mode(const moc_handle *h, const AttenuateParams &a, unsigned grid, size_t smem)
 {
     const bool flat = h->I.axial_exp == 0;
     // 0: table, IEEE division; 1: table, verified fast division; 2: SFU
     const int mode = h->exp_mode == 1 ? 2 : (h->fast_cell_ok ? 1 : 0);
     h->launch_count++;
-#define MOC_LAUNCH(M, F) attenuate_kernel<L, NV4, NS, M, F><<<grid, 128, (M) == 2 ? 0 : smem, h->stream>>>(a)
+#define MOC_LAUNCH(M, F) attenuate_kernel<L, NV4, NS, M, F, GC><<<grid, 128, (M) == 2 ? 0 : smem, h->stream>>>(a)
     if (!flat) {
         if (mode == 0) MOC_LAUNCH(0, false);
         else if (mode == 1) MOC_LAUNCH(1, false);
@@ -644,9 +665,19 @@ static int launch_attenuate(const moc_handle *h, const AttenuateParams &a, long 
     }
     const int tracks_per_block = 4 * (32 / m.L);
     const unsigned grid = (unsigned)((n_tracks + tracks_per_block - 1) / tracks_per_block);
-    const size_t smem = sizeof(float2) * ((size_t)h->table_n + 1);
+    const size_t smem = sizeof(float) * 2 * ((size_t)h->table_n + 1);
+    const int G = h->G;
+    // the group counts of the named configurations get their own instantiation (row strides
+    // become immediates); everything else takes G from the parameters (GC = 0)
+#define MOC_CASE_G(l, v, s, gc) \
+    if (m.L == l && m.NV4 == v && m.NS == s && G == gc) return launch_attenuate_mode<l, v, s, gc>(h, a, grid, smem);
 #define MOC_CASE(l, v, s) \
-    if (m.L == l && m.NV4 == v && m.NS == s) return launch_attenuate_mode<l, v, s>(h, a, grid, smem);
+    if (m.L == l && m.NV4 == v && m.NS == s) return launch_attenuate_mode<l, v, s, 0>(h, a, grid, smem);
+    MOC_CASE_G(8, 3, 1, 104)
+    MOC_CASE_G(8, 3, 1, 100)
+    MOC_CASE_G(8, 4, 0, 128)
+    MOC_CASE_G(8, 2, 0, 64)
+    MOC_CASE_G(8, 1, 0, 32)
     MOC_CASE(8, 3, 1)
     MOC_CASE(8, 4, 0)
     MOC_CASE(8, 3, 0)
@@ -666,6 +697,7 @@ static int launch_attenuate(const moc_handle *h, const AttenuateParams &a, long 
     MOC_CASE(32, 0, 8)
     MOC_CASE(32, 0, 16)
 #undef MOC_CASE
+#undef MOC_CASE_G
     moc_set_error("no attenuation kernel instantiated for lane map L=%d NV4=%d NS=%d", m.L, m.NV4, m.NS);
     return MOC_EINVAL;
 }
@@ -780,8 +812,9 @@ extern "C" int moc_sweep(moc_handle *h, long *segments_processed)
     a.mu = h->d.mu;
     a.psi = h->d.psi;
     a.fine_source = h->d.src;
-    a.fine_flux = h->d.src + (size_t)h->N * h->F * h->G;
-    a.sigT = h->d.src + (size_t)2 * h->N * h->F * h->G;
+    a.fine_flux = h->d.src + (size_t)h->N * h->F * h->Gp;
+    a.sigT = h->d.src + (size_t)2 * h->N * h->F * h->Gp;
+    a.pitch = h->Gp;
     a.table = h->d.table;
     a.table_dx = h->table_dx;
     a.table_rdx = 1.0f / h->table_dx;
@@ -855,7 +888,8 @@ static SourceParams source_params(const moc_handle *h)
 {
     SourceParams p;
     p.fine_source = h->d.src;
-    p.fine_flux = h->d.src + (size_t)h->N * h->F * h->G;
+    p.fine_flux = h->d.src + (size_t)h->N * h->F * h->Gp;
+    p.pitch = h->Gp;
     p.xs = h->d.xs;
     p.scatter = h->d.scatter;
     p.xs_index = h->d.xs_index;
@@ -880,7 +914,7 @@ extern "C" int moc_renormalize(moc_handle *h)
         int rc = allreduce_scalars(h, h->d.scalars, 1);   // solver.c:1190-1195
         if (rc) return rc;
     }
-    const long long cells = h->N * h->F * h->G;
+    const long long cells = h->N * h->F * h->Gp;
     scale_flux_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, h->stream>>>(p, h->d.scalars);
     const long long n = 2 * h->T3 * h->G;
     const long long n4 = n / 4;
@@ -939,13 +973,17 @@ extern "C" int moc_compute_keff(moc_handle *h, float *keff)
 
 // ------------------------------------------------------------------ array access
 
-static int array_span(moc_handle *h, int which, void **ptr, size_t *bytes)
+// `rows` > 0: the array is `rows` rows of the padded source slab starting at slab row `row0`
+static int array_span(moc_handle *h, int which, void **ptr, size_t *bytes, size_t *row0, size_t *rows)
 {
     const size_t T3 = (size_t)h->T3, G = (size_t)h->G, N = (size_t)h->N, F = (size_t)h->F;
+    *rows = 0;
+    *row0 = 0;
+    *ptr = nullptr;
     switch (which) {
-    case MOC_ARR_FINE_SOURCE: *ptr = h->d.src; *bytes = sizeof(float) * N * F * G; return MOC_OK;
-    case MOC_ARR_FINE_FLUX: *ptr = h->d.src + N * F * G; *bytes = sizeof(float) * N * F * G; return MOC_OK;
-    case MOC_ARR_SIGT: *ptr = h->d.src + 2 * N * F * G; *bytes = sizeof(float) * N * G; return MOC_OK;
+    case MOC_ARR_FINE_SOURCE: *row0 = 0; *rows = N * F; *bytes = sizeof(float) * N * F * G; return MOC_OK;
+    case MOC_ARR_FINE_FLUX: *row0 = N * F; *rows = N * F; *bytes = sizeof(float) * N * F * G; return MOC_OK;
+    case MOC_ARR_SIGT: *row0 = 2 * N * F; *rows = N; *bytes = sizeof(float) * N * G; return MOC_OK;
     case MOC_ARR_PSI: *ptr = h->d.psi; *bytes = sizeof(float) * 2 * T3 * G; return MOC_OK;
     case MOC_ARR_Z_HEIGHT: *ptr = h->d.z_height; *bytes = sizeof(float) * T3; return MOC_OK;
     case MOC_ARR_P_WEIGHT: *ptr = h->d.p_weight; *bytes = sizeof(float) * T3; return MOC_OK;
@@ -961,14 +999,15 @@ extern "C" int moc_get_array(moc_handle *h, int which, void *dst, size_t bytes)
     if (!h || !dst) return MOC_EINVAL;
     CUDA_TRY(cudaSetDevice(h->device));
     void *p;
-    size_t n;
-    int rc = array_span(h, which, &p, &n);
+    size_t n, row0, rows;
+    int rc = array_span(h, which, &p, &n, &row0, &rows);
     if (rc) return rc;
     if (bytes != n) {
         moc_set_error("moc_get_array(%d): buffer is %zu bytes, array is %zu", which, bytes, n);
         return MOC_EINVAL;
     }
-    CUDA_TRY(cudaMemcpyAsync(dst, p, n, cudaMemcpyDeviceToHost, h->stream));
+    if (rows) CUDA_TRY(slab_to_host(h, row0, rows, (float *)dst));
+    else CUDA_TRY(cudaMemcpyAsync(dst, p, n, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     return MOC_OK;
 }
@@ -978,14 +1017,15 @@ extern "C" int moc_set_array(moc_handle *h, int which, const void *src, size_t b
     if (!h || !src) return MOC_EINVAL;
     CUDA_TRY(cudaSetDevice(h->device));
     void *p;
-    size_t n;
-    int rc = array_span(h, which, &p, &n);
+    size_t n, row0, rows;
+    int rc = array_span(h, which, &p, &n, &row0, &rows);
     if (rc) return rc;
     if (bytes != n || which == MOC_ARR_SEG_COUNT || which == MOC_ARR_QSR_DIGEST) {
         moc_set_error("moc_set_array(%d): read-only array or size mismatch (%zu vs %zu)", which, bytes, n);
         return MOC_EINVAL;
     }
-    CUDA_TRY(cudaMemcpyAsync(p, src, n, cudaMemcpyHostToDevice, h->stream));
+    if (rows) CUDA_TRY(slab_to_device(h, row0, rows, (const float *)src));
+    else CUDA_TRY(cudaMemcpyAsync(p, src, n, cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     return MOC_OK;
 }
@@ -1023,11 +1063,10 @@ static int download_into(moc_handle *h, const HostLayout &L, Params *P, int what
     if (what == 1) {
         CUDA_TRY(cudaMemcpy2DAsync(L.psi, sizeof(float) * 2 * G, h->d.psi, sizeof(float) * 2 * G, sizeof(float) * G,
                                    T3, cudaMemcpyDeviceToHost, h->stream));
-        CUDA_TRY(cudaMemcpyAsync(L.src + N * F * G, h->d.src + N * F * G, sizeof(float) * N * F * G,
-                                 cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(slab_to_host(h, N * F, N * F, L.src + N * F * G));
     } else {
         CUDA_TRY(cudaMemcpyAsync(L.psi, h->d.psi, sizeof(float) * 2 * T3 * G, cudaMemcpyDeviceToHost, h->stream));
-        CUDA_TRY(cudaMemcpyAsync(L.src, h->d.src, sizeof(float) * (2 * F + 1) * N * G, cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(slab_to_host(h, 0, (2 * F + 1) * N, L.src));
         if (P->leakage)
             CUDA_TRY(cudaMemcpyAsync(P->leakage, h->d.leakage, sizeof(float), cudaMemcpyDeviceToHost, h->stream));
     }
@@ -1382,8 +1421,7 @@ extern "C" float update_sources(Params params, Input I, float keff)
     if (g_resident) m.dirty_all = true;
     else {
         // only fine_source changes
-        const size_t n = sizeof(float) * (size_t)m.h->N * m.h->F * m.h->G;
-        if (cudaMemcpyAsync(L.src, m.h->d.src, n, cudaMemcpyDeviceToHost, m.h->stream) != cudaSuccess ||
+        if (slab_to_host(m.h, 0, (size_t)m.h->N * m.h->F, L.src) != cudaSuccess ||
             cudaStreamSynchronize(m.h->stream) != cudaSuccess) {
             moc_set_error("download of fine_source failed");
             die("update_sources");

@@ -29,7 +29,7 @@
 
 // minimum resident CTAs per SM the attenuation kernel is compiled for (register budget)
 #ifndef MOC_ATT_MIN_BLOCKS
-#define MOC_ATT_MIN_BLOCKS 1
+#define MOC_ATT_MIN_BLOCKS 5
 #endif
 
 namespace moc {
@@ -76,9 +76,10 @@ struct AttenuateParams {
     const float *az_weight;           // [T2]
     const float *mu;                  // [P] (float)cos(polar[j])
     float *psi;                       // [T3][2][G]
-    const float *fine_source;         // [N][fai][G]
-    float *fine_flux;                 // [N][fai][G]
-    const float *sigT;                // [N][G]
+    const float *fine_source;         // [N][fai][pitch]   rows padded to 128 bytes (pitch = G rounded up to 32)
+    float *fine_flux;                 // [N][fai][pitch]
+    const float *sigT;                // [N][pitch]
+    int pitch;
     const float *table;               // [2*table_n]
     float table_dx, table_rdx, table_max, table_half_dx;
     int table_n;
@@ -408,304 +409,7 @@ __global__ void pair_scan_kernel(const unsigned long long *in, unsigned long lon
 }
 
 // ------------------------------------------------------------------ K1: attenuation
-
-// MUFU.RCP / MUFU.EX2 without the range fix-ups of the libdevice wrappers
-__device__ __forceinline__ float rcp_approx(float x)
-{
-    float r;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-}
-__device__ __forceinline__ float ex2_approx(float x)
-{
-    float r;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-}
-
-// The table cell the reference picks for x (solver.c:1448): (int)(x / dx + 0.5f * dx), with an
-// IEEE float division.  EXACT_DIV: the division instruction sequence of __fdiv_rn.
-// !EXACT_DIV: quotient by one Newton step on x * fl(1/dx) (3 instructions); the host only
-// selects this variant after table_cell_check_kernel has verified, for EVERY float in
-// [0, maxVal], that it lands in the same cell.
-template <bool EXACT_DIV>
-__device__ __forceinline__ int table_cell(float x, float dx, float rdx, float half_dx)
-{
-    float q;
-    if (EXACT_DIV) {
-        q = __fdiv_rn(x, dx);
-    } else {
-        q = __fmul_rn(x, rdx);
-        const float rem = __fmaf_rn(-q, dx, x);
-        q = __fmaf_rn(rem, rdx, q);
-    }
-    return __float2int_rz(__fadd_rn(q, half_dx));
-}
-
-// exhaustive check of the fast cell selection: one thread per float bit pattern in [0, bits_max]
-__global__ void table_cell_check_kernel(unsigned int bits_max, float dx, float rdx, float half_dx,
-                                        unsigned long long *mismatches)
-{
-    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-    unsigned int bad = 0;
-    for (unsigned long long b = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; b <= bits_max; b += stride) {
-        const float x = __uint_as_float((unsigned int)b);
-        bad += table_cell<true>(x, dx, rdx, half_dx) != table_cell<false>(x, dx, rdx, half_dx);
-    }
-    if (bad) atomicAdd(mismatches, (unsigned long long)bad);
-}
-
-struct TableConsts {
-    float dx, rdx, half_dx, x_max;
-    int n;   // cells; s_tab[n] = (0, 1): the value of every x > x_max
-};
-
-// E = 1 - exp(-x) and D = exp(-x) = 1 - E.
-//  MODE 0: the reference's linear table, cell chosen exactly as solver.c:1448 does (the slope sign
-//          is the reference's), IEEE division.
-//  MODE 1: the same with the verified fast division.
-//  MODE 2: SFU: MUFU.EX2.
-// All keep the reference's x > maxVal -> 1 rule (solver.c:1444-1445).
-template <int MODE>
-__device__ __forceinline__ void one_minus_exp(float x, const float2 *tab, const TableConsts &tc, float &E, float &D)
-{
-    if (MODE == 2) {
-        const float d = ex2_approx(x * -1.4426950408889634f);
-        const bool big = x > tc.x_max;
-        D = big ? 0.0f : d;
-        E = 1.0f - D;
-    } else {
-        int cell = table_cell<MODE == 0>(x, tc.dx, tc.rdx, tc.half_dx);
-        cell = x > tc.x_max ? tc.n : cell;
-        const float2 line = tab[cell];
-        E = fmaf(line.x, x, line.y);
-        D = 1.0f - E;
-    }
-}
-
-// per-segment scalars of attenuate_fluxes, hoisted out of the group loop
-struct SegmentScalars {
-    float ds;
-    float a1, a2;      // zin/(2dz), zin^2/(2dz^2)          : q0 = y2 + a1 (y1-y3) + a2 (y1-2y2+y3)
-    float b1, b2;      // mu/(2dz), 2 mu zin/(2dz^2)        : q1 mu
-    float b3, b3_3;    // mu^2/(2dz^2), the same / 3         : q2 mu^2
-    float weight;
-};
-
-// one energy group of attenuate_fluxes (solver.c:66-82, 146-279).  Returns the tally.
-// Same formulas, regrouped so that every factor that does not depend on the group is a
-// per-segment scalar and every division is a multiplication by MUFU.RCP(sigT).
-template <int MODE>
-__device__ __forceinline__ float attenuate_quadratic(float y1, float y2, float y3, float sigT, float &psi,
-                                                     const SegmentScalars &k, const float2 *tab,
-                                                     const TableConsts &tc)
-{
-    const float d = y1 - y3;
-    const float e = fmaf(-2.f, y2, y1 + y3);
-    const float q0 = fmaf(k.a2, e, fmaf(k.a1, d, y2));
-    const float q1m = fmaf(k.b2, e, k.b1 * d);          // q1 * mu
-    const float q2m = k.b3 * e;                         // q2 * mu^2
-    const float q2m3 = k.b3_3 * e;                      // q2 * mu^2 / 3
-    const float tau = sigT * k.ds;
-    float E, D;
-    one_minus_exp<MODE>(tau, tab, tc, E, D);
-    const float r1 = rcp_approx(sigT);
-    const float r2 = r1 * r1;
-    const float r3 = r2 * r1;
-    const float r4 = r2 * r2;
-    // solver.c:175-176 exactly as parenthesised there
-    const float reuse = fmaf(2.f, E * r3, tau * (tau - 2.f));
-    float in = fmaf(q0, tau, fmaf(sigT, psi, -q0) * E) * r2;
-    in = fmaf(q1m, reuse, in);
-    const float cubic = fmaf(-6.f, E, tau * fmaf(tau, tau - 3.f, 6.f));
-    in = fmaf(q2m3, cubic * r4, in);
-    float out = (q0 * E) * r1;
-    out = fmaf(q1m * r2, tau - E, out);
-    out = fmaf(q2m, reuse, out);
-    psi = fmaf(psi, D, out);
-    return k.weight * in;
-}
-
-// one energy group of attenuate_FSR_fluxes (solver.c:1104-1115)
-template <int MODE>
-__device__ __forceinline__ float attenuate_flat(float src, float sigT, float &psi, const SegmentScalars &k,
-                                                const float2 *tab, const TableConsts &tc)
-{
-    const float tau = sigT * k.ds;
-    float E, D;
-    one_minus_exp<MODE>(tau, tab, tc, E, D);
-    const float q = __fdiv_rn(src, sigT);   // flat source: the difference psi - q cancels, keep the division exact
-    const float dpsi = (psi - q) * E;
-    psi -= dpsi;
-    return k.weight * dpsi;
-}
-
-// fine_flux is only ever reduced into by this kernel (never read), so the reductions carry no
-// "memory" clobber: the compiler may hoist the next segment's loads above them.
-__device__ __forceinline__ void red_add_v4(float *addr, float4 v)
-{
-    // sm_90+: one 16-byte reduction instead of four 4-byte ones
-    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y),
-                 "f"(v.z), "f"(v.w));
-}
-__device__ __forceinline__ void red_add(float *addr, float v)
-{
-    asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v));
-}
-
-// L lanes cooperate on one 3D track (32/L tracks per warp).  Lane `lit` of a track
-// owns NV4 float4 group-quads  g = 4*(lit + L*v) ..+3   and NS single groups
-// g = 4*L*NV4 + lit + L*s  (so G=104 -> L=8, NV4=3, NS=1 uses every lane fully).
-// The angular flux of the track lives in registers for the whole track.
-template <int L, int NV4, int NS, int MODE, bool FLAT>
-__global__ void __launch_bounds__(128, MOC_ATT_MIN_BLOCKS) attenuate_kernel(const AttenuateParams a)
-{
-    extern __shared__ float2 s_tab[];
-    if (MODE != 2) {
-        for (int e = threadIdx.x; e < a.table_n; e += blockDim.x)
-            s_tab[e] = make_float2(a.table[2 * e], a.table[2 * e + 1]);
-        if (threadIdx.x == 0) s_tab[a.table_n] = make_float2(0.f, 1.f);
-        __syncthreads();
-    }
-    TableConsts tc;
-    tc.dx = a.table_dx; tc.rdx = a.table_rdx; tc.half_dx = a.table_half_dx; tc.x_max = a.table_max;
-    tc.n = a.table_n;
-    constexpr int TPW = 32 / L;
-    const int lane = threadIdx.x & 31;
-    const int lit = lane % L;
-    const int G = a.G;
-    const long long t = a.first_track + ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * TPW + lane / L;
-    const bool valid = t < a.end_track;
-
-    uint32_t n_rec = 0, at = 0;
-    SegmentScalars sc;
-    sc.ds = 0.f; sc.a1 = sc.a2 = sc.b1 = sc.b2 = sc.b3 = sc.b3_3 = 0.f; sc.weight = 0.f;
-    float mu = 0.f;
-    if (valid) {
-        n_rec = a.seg_count[t];
-        at = a.track_off[t - a.first_track];
-        const long long pair = t / a.Z;
-        const int j = (int)(pair % a.P);
-        const long long i = pair / a.P;
-        mu = a.mu[j];
-        float w0 = __fmul_rn(a.p_weight[t], a.az_weight[i]);   // solver.c:49
-        if (FLAT) w0 = __fmul_rn(w0, mu);                      // solver.c:1064
-        sc.weight = w0;
-        sc.b1 = mu * a.inv_2dz;
-        sc.b3 = mu * mu * a.inv_2dz2;
-        sc.b3_3 = sc.b3 * (1.f / 3.f);
-    }
-    const float two_mu_c = 2.f * mu * a.inv_2dz2;
-    unsigned int longest = n_rec;
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-        unsigned int o = __shfl_xor_sync(0xffffffffu, longest, d);
-        longest = o > longest ? o : longest;
-    }
-
-    // group ownership
-    const int g_tail = 4 * L * NV4;
-    float4 psi4[NV4 > 0 ? NV4 : 1];
-    float psi1[NS > 0 ? NS : 1];
-    float *psi_row = a.psi + (size_t)2 * (size_t)(valid ? t : 0) * G;
-#pragma unroll
-    for (int v = 0; v < NV4; v++) {
-        const int g = 4 * (lit + L * v);
-        psi4[v] = (valid && g < G) ? *reinterpret_cast<const float4 *>(psi_row + g) : make_float4(0, 0, 0, 0);
-    }
-#pragma unroll
-    for (int s = 0; s < NS; s++) {
-        const int g = g_tail + lit + L * s;
-        psi1[s] = (valid && g < G) ? psi_row[g] : 0.f;
-    }
-
-    // the record of the next segment is fetched one iteration ahead
-    const float *rec_ds = a.rec_ds + at;
-    const float *rec_zin = a.rec_zin + at;
-    const uint32_t *rec_code = a.rec_code + at;
-    float next_ds = 0.f, next_zin = 0.f;
-    uint32_t next_code = 0;
-    if (n_rec > 0) {
-        next_ds = __ldg(rec_ds);
-        next_zin = __ldg(rec_zin);
-        next_code = __ldg(rec_code);
-    }
-
-    for (unsigned int sgm = 0; sgm < longest; sgm++) {
-        if (sgm < n_rec) {
-            sc.ds = next_ds;
-            const float zin = next_zin;
-            const uint32_t code = next_code;
-            if (sgm + 1 < n_rec) {
-                next_ds = __ldg(rec_ds + sgm + 1);
-                next_zin = __ldg(rec_zin + sgm + 1);
-                next_code = __ldg(rec_code + sgm + 1);
-            }
-            sc.a1 = zin * a.inv_2dz;
-            sc.a2 = zin * zin * a.inv_2dz2;
-            sc.b2 = two_mu_c * zin;
-            const uint32_t qsr = code & 0xffffffu;
-            const uint32_t r0 = (code >> 24) & 63u;
-            const uint32_t which = code >> 30;
-            const size_t row0 = (size_t)qsr * a.fai + r0;
-            const float *ya = a.fine_source + row0 * G;
-            const float *st = a.sigT + (size_t)qsr * G;
-            float *fl = a.fine_flux + (row0 + which) * G;
-#pragma unroll
-            for (int v = 0; v < NV4; v++) {
-                const int g = 4 * (lit + L * v);
-                if (g < G) {
-                    const float4 s4 = __ldg(reinterpret_cast<const float4 *>(st + g));
-                    float4 tally;
-                    if (FLAT) {
-                        const float4 y = __ldg(reinterpret_cast<const float4 *>(ya + g));
-                        tally.x = attenuate_flat<MODE>(y.x, s4.x, psi4[v].x, sc, s_tab, tc);
-                        tally.y = attenuate_flat<MODE>(y.y, s4.y, psi4[v].y, sc, s_tab, tc);
-                        tally.z = attenuate_flat<MODE>(y.z, s4.z, psi4[v].z, sc, s_tab, tc);
-                        tally.w = attenuate_flat<MODE>(y.w, s4.w, psi4[v].w, sc, s_tab, tc);
-                    } else {
-                        const float4 y1 = __ldg(reinterpret_cast<const float4 *>(ya + g));
-                        const float4 y2 = __ldg(reinterpret_cast<const float4 *>(ya + G + g));
-                        const float4 y3 = __ldg(reinterpret_cast<const float4 *>(ya + 2 * G + g));
-                        tally.x = attenuate_quadratic<MODE>(y1.x, y2.x, y3.x, s4.x, psi4[v].x, sc, s_tab, tc);
-                        tally.y = attenuate_quadratic<MODE>(y1.y, y2.y, y3.y, s4.y, psi4[v].y, sc, s_tab, tc);
-                        tally.z = attenuate_quadratic<MODE>(y1.z, y2.z, y3.z, s4.z, psi4[v].z, sc, s_tab, tc);
-                        tally.w = attenuate_quadratic<MODE>(y1.w, y2.w, y3.w, s4.w, psi4[v].w, sc, s_tab, tc);
-                    }
-                    red_add_v4(fl + g, tally);
-                }
-            }
-#pragma unroll
-            for (int s = 0; s < NS; s++) {
-                const int g = g_tail + lit + L * s;
-                if (g < G) {
-                    const float s1 = __ldg(st + g);
-                    float tally;
-                    if (FLAT) {
-                        tally = attenuate_flat<MODE>(__ldg(ya + g), s1, psi1[s], sc, s_tab, tc);
-                    } else {
-                        tally = attenuate_quadratic<MODE>(__ldg(ya + g), __ldg(ya + G + g), __ldg(ya + 2 * G + g),
-                                                          s1, psi1[s], sc, s_tab, tc);
-                    }
-                    red_add(fl + g, tally);
-                }
-            }
-        }
-    }
-
-    if (valid) {
-#pragma unroll
-        for (int v = 0; v < NV4; v++) {
-            const int g = 4 * (lit + L * v);
-            if (g < G) *reinterpret_cast<float4 *>(psi_row + g) = psi4[v];
-        }
-#pragma unroll
-        for (int s = 0; s < NS; s++) {
-            const int g = g_tail + lit + L * s;
-            if (g < G) psi_row[g] = psi1[s];
-        }
-    }
-}
+#include "moc_attenuate.cuh"
 
 // ------------------------------------------------------------------ exact pairwise sums
 
@@ -771,8 +475,9 @@ __device__ float pairwise_sum_cta(const float *v, long long n, float *slots /*[2
 // ------------------------------------------------------------------ K2..K4
 
 struct SourceParams {
-    float *fine_source;     // [N][fai][G]
-    float *fine_flux;       // [N][fai][G]
+    float *fine_source;     // [N][fai][pitch]
+    float *fine_flux;       // [N][fai][pitch]
+    int pitch;              // row pitch in floats (G rounded up to 32: 128-byte aligned rows)
     const float *xs;        // [X][G][3]
     const float *scatter;   // [X][G][G]
     const int *xs_index;    // [N]
@@ -786,13 +491,13 @@ __global__ void region_fission_rate_kernel(const SourceParams p, float *per_regi
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= p.N) return;
-    const float *flux = p.fine_flux + (size_t)i * p.fai * p.G;
+    const float *flux = p.fine_flux + (size_t)i * p.fai * p.pitch;
     const float *x = p.xs + (size_t)p.xs_index[i] * p.G * 3;
     const float vol = p.vol[i];
-    const int G = p.G;
+    const int G = p.G, W = p.pitch;
     auto per_fine = [&](long long jf) {
         auto per_group = [&](long long g) {
-            return __fmul_rn(__fmul_rn(flux[jf * G + g], vol), x[3 * g]);
+            return __fmul_rn(__fmul_rn(flux[jf * W + g], vol), x[3 * g]);
         };
         return pairwise_sum(per_group, 0, G);
     };
@@ -804,12 +509,12 @@ __global__ void region_reaction_rates_kernel(const SourceParams p, float *absorp
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= p.N) return;
-    const float *flux = p.fine_flux + (size_t)i * p.fai * p.G;
+    const float *flux = p.fine_flux + (size_t)i * p.fai * p.pitch;
     const float *x = p.xs + (size_t)p.xs_index[i] * p.G * 3;
-    const int G = p.G;
+    const int G = p.G, W = p.pitch;
     for (int col = 0; col < 2; col++) {
         auto per_fine = [&](long long jf) {
-            auto per_group = [&](long long g) { return __fmul_rn(x[3 * g + col], flux[jf * G + g]); };
+            auto per_group = [&](long long g) { return __fmul_rn(x[3 * g + col], flux[jf * W + g]); };
             return pairwise_sum(per_group, 0, G);
         };
         const float r = pairwise_sum(per_fine, 0, p.fai);
@@ -829,7 +534,7 @@ __global__ void pairwise_reduce_kernel(const float *v, long long n, float *out, 
 // fine_flux *= norm * 4 pi fai / vol   (solver.c:1207-1214); scal[0] = total fission rate
 __global__ void scale_flux_kernel(const SourceParams p, const float *scal)
 {
-    const long long per = (long long)p.fai * p.G;
+    const long long per = (long long)p.fai * p.pitch;   // padding columns hold zeros and stay zero
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= p.N * per) return;
     const float norm = (float)(1.0 / (double)scal[0]);                     // solver.c:1203
@@ -862,8 +567,8 @@ __global__ void update_sources_kernel(const SourceParams p, float inverse_k, flo
     const long long row = blockIdx.x;          // i * fai + j
     const long long i = row / p.fai;
     const int G = p.G;
-    const float *flux = p.fine_flux + (size_t)row * G;
-    float *q = p.fine_source + (size_t)row * G;
+    const float *flux = p.fine_flux + (size_t)row * p.pitch;
+    float *q = p.fine_source + (size_t)row * p.pitch;
     const int material = p.xs_index[i];
     const float *x = p.xs + (size_t)material * G * 3;
     const float *S = p.scatter + (size_t)material * G * G;
