@@ -6,4 +6,4 @@ This Python package only binds that library for tests and benchmarks.
 """
 from . import api  # noqa: F401
 from .api import (DeviceProblem, HostProblem, MocError, default_input, derive,  # noqa: F401
-                  device_count, input_from_values, make_grid, small_input)
+                  device_count, input_from_values, make_grid, read_input_file, small_input)

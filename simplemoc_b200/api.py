@@ -61,6 +61,12 @@ class CommGrid(C.Structure):
         "z_pos_src", "z_pos_dest", "z_neg_src", "z_neg_dest")]
 
 
+class ExchangeOp(C.Structure):
+    """moc_exchange_op: one chunk of the boundary exchange schedule (src/comms.c:100-183)"""
+    _fields_ = [("offset", C.c_longlong), ("count", C.c_longlong), ("round", C.c_int),
+                ("direction", C.c_int), ("send_to", C.c_int), ("recv_from", C.c_int)]
+
+
 class SweepTiming(C.Structure):
     _fields_ = [("count_ms", C.c_float), ("scan_ms", C.c_float), ("fill_ms", C.c_float),
                 ("attenuate_ms", C.c_float), ("total_ms", C.c_float),
@@ -85,7 +91,7 @@ EXPORTED = [
     "moc_renormalize", "moc_update_sources", "moc_compute_keff", "moc_exchange",
     "moc_get_sweep_timing", "moc_get_array", "moc_set_array", "moc_download", "moc_upload",
     "moc_get_leakage", "moc_synchronize", "moc_get_stream", "moc_get_launch_count", "moc_comm_get_unique_id", "moc_comm_init",
-    "moc_make_grid", "moc_last_error", "moc_device_count", "moc_set_default_input",
+    "moc_make_grid", "moc_exchange_plan", "moc_last_error", "moc_device_count", "moc_set_default_input",
     "moc_set_small_input", "moc_read_input_file", "moc_read_CLI",
     "moc_calculate_derived_inputs", "moc_est_mem_usage", "moc_build_tracks",
     "moc_free_tracks", "moc_time_per_intersection", "moc_params_get", "moc_params_set",
@@ -146,6 +152,8 @@ def lib():
     L.moc_comm_get_unique_id.argtypes = [C.c_char_p]
     L.moc_comm_init.argtypes = [vp, C.c_int, C.c_int, C.c_char_p]
     L.moc_make_grid.argtypes = [C.c_int] * 4 + [C.POINTER(CommGrid)]
+    L.moc_exchange_plan.restype = C.c_long
+    L.moc_exchange_plan.argtypes = [ip, C.POINTER(CommGrid), C.POINTER(ExchangeOp), C.c_long]
     # drop-in names (structures by value where the reference passes them by value)
     L.transport_sweep.restype = None
     L.transport_sweep.argtypes = [C.POINTER(Params), ip]

@@ -371,3 +371,4 @@ __global__ void __launch_bounds__(128, MOC_ATT_MIN_BLOCKS) attenuate_kernel(cons
         }
     }
 }
+

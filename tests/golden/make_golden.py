@@ -21,7 +21,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(HERE))
 from oracle_lib import CASES, RefCase, ensure_ref_built  # noqa: E402
 
-SEEDS = {"tiny": 11, "mini104": 11, "tiny_flat": 11, "odd": 11, "mini_default_in": 11}
+SEEDS = {name: 11 for name in CASES}
 
 
 def sha(a):

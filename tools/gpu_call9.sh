@@ -1,0 +1,3 @@
+python -m pytest tests -m gpu -q -x 2>&1 | tail -8
+python tools/probe.py default 2>&1 | grep -v "^  renorm" | tee gpurun_out/probe9.log
+ncu --set full --clock-control none --import-source on -k regex:attenuate -s 1 -c 1 -o gpurun_out/prof_att6_staged -f python bench.py --limit-tracks-2d 2000 --steps 1 --warmup 1 --no-e2e --no-cpu-baseline > gpurun_out/prof_att6.log 2>&1
