@@ -154,6 +154,17 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def finite(obj):
+    """strict JSON has no NaN/Infinity: non-finite floats become null"""
+    if isinstance(obj, float):
+        return obj if obj == obj and abs(obj) != float("inf") else None
+    if isinstance(obj, dict):
+        return {k: finite(v) for k, v in obj.items()}
+    if isinstance(obj, (list, tuple)):
+        return [finite(v) for v in obj]
+    return obj
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -266,7 +277,7 @@ def run_reference(args):
             "ns_per_integration": 1e9 / value, "cpu_baseline": desc,
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(finite(line), allow_nan=False), flush=True)
 
 
 # ------------------------------------------------------------------ the CUDA path
@@ -323,7 +334,12 @@ def run_moc(args):
         if world > 1:
             dev.exchange(grid)
         dev.renormalize()
-        dev.update_sources(state["keff"])
+        # main.c:81,89 feeds each iteration's k-eff to the next update_sources.  With neighbours the
+        # reference adds UN-normalised boundary flux sums to the leakage (comms.c:120) and never
+        # resets it, so k = fission/(absorption+leakage) collapses after one iteration (it runs
+        # exactly one, main.c:41); keep the source scale finite so later steps time real numbers
+        k_in = state["keff"]
+        dev.update_sources(k_in if (k_in == k_in and 1e-2 < abs(k_in) < 1e2) else 1.0)
         state["keff"] = dev.compute_keff()
         if accumulate:
             t = dev.timing()
@@ -409,7 +425,7 @@ def run_moc(args):
                            "l2": "inputs larger than L2 (12.9 GB angular flux + 23 GB segment records "
                                  "streamed per step); no flush",
                            "host_build_s": round(build_s, 1)},
-                "ns_per_integration": 1e9 / value, "keff": state["keff"],
+                "ns_per_integration": 1e9 / value, "keff": state["keff"], "leakage": dev.leakage,
                 "sweep_ms": state["sweep_ms"] / n_launch,
                 "phases_ms": {"count": state["count_ms"] / n_launch, "fill": state["fill_ms"] / n_launch,
                               "attenuate": state["att_ms"] / n_launch},
@@ -417,7 +433,7 @@ def run_moc(args):
                 "cpu_baseline": cpu}
         if args.limit_tracks_2d:
             line["config"]["limit_tracks_2d"] = args.limit_tracks_2d
-        print(json.dumps(line), flush=True)
+        print(json.dumps(finite(line), allow_nan=False), flush=True)
     dev.close()
     host.close()
     if dist is not None:

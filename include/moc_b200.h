@@ -162,6 +162,14 @@ float compute_keff(Params params, Input I, CommGrid grid);
  * when any neighbour is not -1. */
 void fast_transfer_boundary_fluxes(Params params, Input I, CommGrid grid);
 
+/* What the reference takes from process-global state, the drop-in names take from here:
+ * the seed and position of the random stream (the reference: srand(time(NULL)) + the rand()
+ * calls made so far), the exponential mode (MOC_OPT_EXP_MODE) and sizeof(Source) of the caller
+ * (48, or 56 when it was compiled with -DOPENMP).  Applies to mirrors created afterwards. */
+void moc_dropin_configure(unsigned long long seed, unsigned long long rand_base, int exp_mode,
+                          int source_stride);
+/* CUDA device the drop-in names create their mirror on (cudaSetDevice) */
+int moc_set_device(int device);
 /* 1: keep results on the device between the calls above; 0 (default): write back */
 void moc_set_resident(int on);
 /* download everything the phases run so far have mutated into the host Params */
@@ -262,6 +270,9 @@ typedef struct {
     int send_to, recv_from;
 } moc_exchange_op;
 long moc_exchange_plan(const Input *I, const CommGrid *grid, moc_exchange_op *ops, long max_ops);
+
+/* the handle behind a Params used through the drop-in names (timing queries, moc_comm_init) */
+moc_handle *moc_handle_of(Params *params);
 
 const char *moc_last_error(void);
 int moc_device_count(void);

@@ -1344,6 +1344,14 @@ static int g_dropin_exp_mode = 0, g_dropin_source_stride = 48;
 
 extern "C" void moc_set_resident(int on) { g_resident = on ? 1 : 0; }
 
+extern "C" int moc_set_device(int device)
+{
+    int rc = require_device(device);
+    if (rc) return rc;
+    CUDA_TRY(cudaSetDevice(device));
+    return MOC_OK;
+}
+
 // options applied to mirrors created by the drop-in entry points
 extern "C" void moc_dropin_configure(unsigned long long seed, unsigned long long rand_base, int exp_mode,
                                      int source_stride)

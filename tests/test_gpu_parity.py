@@ -123,3 +123,46 @@ def test_sfu_mode_against_exact_exp_oracle(built):
     print(f"SFU vs expf oracle: fine_flux rel-L2 = {err:.3e}")
     assert np.isfinite(err)
     dev.close(); host.close(); oracle.close()
+
+
+def test_dropin_names_on_the_reference_own_structures(built):
+    """The drop-in C-ABI (transport_sweep, renormalize_flux, update_sources, compute_keff under the
+    reference's names) driven with the pointer-rich Params/Input that the UNMODIFIED reference's
+    build_tracks() allocated (oracle/_ref): results land in the reference's own buffers."""
+    import ctypes as C
+    from oracle_lib import RefCase, ref_available
+    if not ref_available():
+        pytest.skip("oracle/_ref did not travel")
+    L = api.lib()
+    vals, seed = CASES["mini104"], 13
+    mine, theirs = RefCase(vals, seed=seed), RefCase(vals, seed=seed)
+    n_cpu = theirs.sweep()                                           # the reference, on the CPU
+    L.moc_dropin_configure(seed, mine.init_rand_calls, 0, 48)
+    L.moc_set_resident(0)
+    params = api.Params.from_address(mine._ptr("params"))
+    inp = api.Input.from_address(mine._ptr("input_mut"))
+    L.transport_sweep(C.byref(params), C.byref(inp))                 # the library, on the GPU
+    assert inp.segments_processed == n_cpu
+    assert np.array_equal(mine.z_height, theirs.z_height)
+    for name in ("fine_flux", "psi"):
+        a, b = getattr(mine, name), getattr(theirs, name)
+        assert rel_l2(a, b) <= TOL and frac_within(a, b, TOL) >= FRAC, name
+    grid = api.CommGrid(*([-1] * 12))
+    L.renormalize_flux(params, inp, grid); theirs.renormalize()
+    res = L.update_sources(params, inp, 1.0); res_cpu = theirs.update_sources(1.0)
+    assert abs(res - res_cpu) <= 1e-3 * abs(res_cpu)
+    k, k_cpu = L.compute_keff(params, inp, grid), theirs.compute_keff()
+    assert abs(k - k_cpu) <= TOL * abs(k_cpu)
+    for name in ("fine_flux", "psi", "fine_source"):
+        a, b = getattr(mine, name), getattr(theirs, name)
+        assert rel_l2(a, b) <= TOL, name
+    # resident mode: nothing comes back until moc_sync_to_host
+    L.moc_set_resident(1)
+    before = mine.fine_flux.copy()
+    L.transport_sweep(C.byref(params), C.byref(inp)); theirs.sweep()
+    assert np.array_equal(mine.fine_flux, before)
+    assert L.moc_sync_to_host(C.byref(params)) == 0
+    assert rel_l2(mine.fine_flux, theirs.fine_flux) <= TOL
+    L.moc_set_resident(0)
+    assert L.moc_release(C.byref(params)) == 0
+    mine.close(); theirs.close()
