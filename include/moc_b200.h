@@ -200,7 +200,9 @@ enum {
     MOC_OPT_RAND_BASE = 3,      /* rand() calls made before the sweep (serial-stream position)   */
     MOC_OPT_BATCH_SEGMENTS = 4, /* max 3D segments staged per batch (scratch size), default 2^28 */
     MOC_OPT_SOURCE_STRIDE = 5,  /* sizeof(Source) of the caller: 48 (default) or 56 (OPENMP)     */
-    MOC_OPT_LANES_PER_TRACK = 6 /* override the lane mapping of the attenuation kernel (0=auto)  */
+    MOC_OPT_LANES_PER_TRACK = 6,/* override the lane mapping of the attenuation kernel (0=auto)  */
+    MOC_OPT_STREAM_CHUNKS = 7   /* z-stack chunks the host-side transport_sweep moves the angular
+                                   flux in (copies overlap kernels), default 16                  */
 };
 
 /* arrays for moc_get_array / moc_set_array (flat, the reference's slab order) */

@@ -127,6 +127,10 @@ struct moc_handle {
     DeviceBuffers d;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[8] = {};
+    // host-streamed sweep (drop-in transport_sweep on host structures): copies overlap the kernels
+    cudaStream_t up_stream = nullptr, down_stream = nullptr;
+    std::vector<cudaEvent_t> ev_pool;   // per-batch events, grown on demand
+    int stream_chunks = 16;             // z-stack chunks the flux slab travels in
     // options
     int exp_mode = 0;
     unsigned long long seed = 1, rand_base = 0;
@@ -387,6 +391,10 @@ extern "C" int moc_destroy(moc_handle *h)
     free_buffers(h->d);
     for (auto &e : h->ev)
         if (e) cudaEventDestroy(e);
+    for (auto &e : h->ev_pool)
+        if (e) cudaEventDestroy(e);
+    if (h->up_stream) cudaStreamDestroy(h->up_stream);
+    if (h->down_stream) cudaStreamDestroy(h->down_stream);
     if (h->pair_base_pinned) cudaFreeHost(h->pair_base_pinned);
     if (h->recv_stage) cudaFree(h->recv_stage);
     if (h->exch_table) cudaFree(h->exch_table);
@@ -521,6 +529,10 @@ extern "C" int moc_set_option(moc_handle *h, int option, long value)
         if (value != 0 && value != 4 && value != 8 && value != 16 && value != 32) break;
         h->lanes_override = (int)value;
         return MOC_OK;
+    case MOC_OPT_STREAM_CHUNKS:
+        if (value < 1 || value > 4096) break;
+        h->stream_chunks = (int)value;
+        return MOC_OK;
     case 100: h->want_digest = value != 0; return MOC_OK;   // MOC_OPT_DIGEST (diagnostic)
     case 101:                                                // MOC_OPT_EXACT_DIV (diagnostic): 1 = never use the fast cell selection
         if (value) h->fast_cell_ok = 0;
@@ -540,6 +552,7 @@ extern "C" long moc_get_option(moc_handle *h, int option)
     case MOC_OPT_BATCH_SEGMENTS: return (long)h->batch_segments;
     case MOC_OPT_SOURCE_STRIDE: return h->source_stride;
     case MOC_OPT_LANES_PER_TRACK: return h->lanes_override;
+    case MOC_OPT_STREAM_CHUNKS: return h->stream_chunks;
     case 100: return h->want_digest;
     case 101: return !h->fast_cell_ok;
     }
@@ -728,20 +741,78 @@ static int ensure_record_capacity(moc_handle *h, long long records, long long tr
     return MOC_OK;
 }
 
-extern "C" int moc_sweep(moc_handle *h, long *segments_processed)
+// events of the per-batch pipeline, created on demand and kept for the next sweep
+static int event_at(moc_handle *h, size_t idx, cudaEvent_t *out)
 {
-    if (!h) {
-        moc_set_error("moc_sweep: null handle");
-        return MOC_EINVAL;
+    while (h->ev_pool.size() <= idx) {
+        cudaEvent_t e = nullptr;
+        CUDA_TRY(cudaEventCreate(&e));
+        h->ev_pool.push_back(e);
     }
+    *out = h->ev_pool[idx];
+    return MOC_OK;
+}
+
+// One transport sweep.  io == nullptr: the problem is resident in HBM (moc_sweep).
+// io != nullptr: the host structures are authoritative (the drop-in transport_sweep):
+// the Track image and the source slab are uploaded first, the forward angular flux
+// travels in `stream_chunks` chunks of whole z-stacks on a copy stream while earlier
+// chunks are swept, and every finished chunk (flux rows, ray heights) goes back on a
+// third stream -- host<->device copies overlap the kernels in both directions.
+static int sweep_core(moc_handle *h, long *segments_processed, const HostLayout *io)
+{
     CUDA_TRY(cudaSetDevice(h->device));
     const long long pairs = h->T2 * h->P;
+    const size_t G = (size_t)h->G;
     cudaEvent_t e_start = h->ev[0], e_count = h->ev[1], e_scan = h->ev[2], e_end = h->ev[3];
     long launches = 0;
+    int rc;
+
+    // ---- chunks of whole z-stacks (only the host-streamed sweep has more than one)
+    std::vector<long long> chunk_first;   // first pair of every chunk, plus the end
+    {
+        long long n = io ? std::min<long long>(std::max(h->stream_chunks, 1), std::max<long long>(pairs, 1)) : 1;
+        const long long per = (pairs + n - 1) / std::max<long long>(n, 1);
+        for (long long p = 0; p < pairs; p += std::max<long long>(per, 1)) chunk_first.push_back(p);
+        chunk_first.push_back(pairs);
+    }
+    const size_t n_chunks = chunk_first.size() - 1;
+    size_t ev_next = 0;
+    std::vector<cudaEvent_t> ev_up(n_chunks);
+
+    CUDA_TRY(cudaEventRecord(e_start, h->stream));
+    if (io) {
+        if (!h->up_stream) CUDA_TRY(cudaStreamCreateWithFlags(&h->up_stream, cudaStreamNonBlocking));
+        if (!h->down_stream) CUDA_TRY(cudaStreamCreateWithFlags(&h->down_stream, cudaStreamNonBlocking));
+        // what the counting pass needs first: ray heights (inside the 40-byte Track image) and,
+        // for the attenuation, the source slab
+        cudaEvent_t e_img;
+        if ((rc = event_at(h, ev_next++, &e_img))) return rc;
+        CUDA_TRY(cudaStreamWaitEvent(h->up_stream, e_start, 0));
+        CUDA_TRY(cudaMemcpyAsync(h->d.track_image, io->tracks, sizeof(TrackImage) * (size_t)h->T3,
+                                 cudaMemcpyHostToDevice, h->up_stream));
+        CUDA_TRY(cudaMemcpy2DAsync(h->d.src, sizeof(float) * h->Gp, io->src, sizeof(float) * G, sizeof(float) * G,
+                                   (size_t)(2 * h->F + 1) * (size_t)h->N, cudaMemcpyHostToDevice, h->up_stream));
+        CUDA_TRY(cudaEventRecord(e_img, h->up_stream));
+        for (size_t c = 0; c < n_chunks; c++) {
+            const size_t t0 = (size_t)chunk_first[c] * h->Z, t1 = (size_t)chunk_first[c + 1] * h->Z;
+            // forward rows only: row pitch 2*G floats on both sides
+            CUDA_TRY(cudaMemcpy2DAsync(h->d.psi + 2 * t0 * G, sizeof(float) * 2 * G, io->psi + 2 * t0 * G,
+                                       sizeof(float) * 2 * G, sizeof(float) * G, t1 - t0, cudaMemcpyHostToDevice,
+                                       h->up_stream));
+            if ((rc = event_at(h, ev_next++, &ev_up[c]))) return rc;
+            CUDA_TRY(cudaEventRecord(ev_up[c], h->up_stream));
+        }
+        CUDA_TRY(cudaStreamWaitEvent(h->stream, e_img, 0));
+        const int threads = 256;
+        unpack_tracks_kernel<<<(unsigned)((h->T3 + threads - 1) / threads), threads, 0, h->stream>>>(
+            h->d.track_image, h->T3, h->d.p_weight, h->d.z_height);
+        h->launch_count++;
+        launches++;
+    }
 
     // ---- pass 1: segment counts per ray and per (2D track, polar angle) stack
     WalkParams w = walk_params(h);
-    CUDA_TRY(cudaEventRecord(e_start, h->stream));
     if (h->want_digest) cudaMemsetAsync(h->d.digest, 0, sizeof(unsigned long long) * 4, h->stream);
     launch_walk<false>(h, w, pairs);
     launches++;
@@ -757,47 +828,51 @@ extern "C" int moc_sweep(moc_handle *h, long *segments_processed)
     const unsigned long long *base = h->pair_base_pinned;
     const unsigned long long total = base[pairs];
 
-    // ---- batches of whole stacks whose records fit the staging buffers
-    long long cap = h->batch_segments;
-    if (cap <= 0 && (long long)total <= h->rec_capacity) {
-        cap = h->rec_capacity;   // the staging buffers of the previous sweep are large enough
-    } else if (cap <= 0) {
-        size_t free_b = 0, total_b = 0;
-        CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
-        free_b += (size_t)h->rec_capacity * 12;   // what we already hold can be reused
-        cap = (long long)((double)free_b * 0.7 / 12.0);
-        if (cap > (1ll << 31)) cap = 1ll << 31;
-    }
-    unsigned long long largest_pair = 0;
+    // ---- batches of whole stacks whose records fit the staging buffers (never across a chunk)
+    unsigned long long largest_pair = 0, largest_chunk = 0;
     for (long long p = 0; p < pairs; p++) largest_pair = std::max(largest_pair, base[p + 1] - base[p]);
-    if ((unsigned long long)cap < largest_pair) cap = (long long)largest_pair;
-    if (cap >= (1ll << 32)) cap = (1ll << 32) - 1;
+    for (size_t c = 0; c < n_chunks; c++)
+        largest_chunk = std::max(largest_chunk, base[chunk_first[c + 1]] - base[chunk_first[c]]);
     if (largest_pair >= (1ull << 32)) {
         moc_set_error("a single z-stack produces %llu segments (> 2^32)", largest_pair);
         return MOC_EINVAL;
     }
     // 2 % headroom: the segment count drifts from sweep to sweep (stale ray heights, solver.c:514-523)
     // and re-allocating multi-GB staging buffers costs hundreds of milliseconds
-    long long need = (long long)std::min<unsigned long long>(total + total / 50 + 1024, (unsigned long long)cap);
-    if (need > (1ll << 32) - 1) need = (1ll << 32) - 1;
-    // the largest batch in tracks
-    std::vector<std::pair<long long, long long>> batches;
-    {
-        long long p = 0;
-        while (p < pairs) {
-            long long q = p;
+    const unsigned long long want = largest_chunk + largest_chunk / 50 + 1024;
+    long long cap = h->batch_segments;
+    if (cap <= 0 && (long long)largest_chunk <= h->rec_capacity) {
+        cap = h->rec_capacity;   // the staging buffers of the previous sweep are large enough
+    } else if (cap <= 0) {
+        size_t free_b = 0, total_b = 0;
+        CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+        free_b += (size_t)h->rec_capacity * 12;   // what we already hold can be reused
+        cap = (long long)((double)free_b * 0.7 / 12.0);
+    }
+    if ((unsigned long long)cap < largest_pair) cap = (long long)largest_pair;
+    if (cap >= (1ll << 32)) cap = (1ll << 32) - 1;
+    long long need = (long long)std::min<unsigned long long>(want, (unsigned long long)cap);
+    struct Batch {
+        long long first, end;
+        size_t chunk;
+        bool last_of_chunk;
+    };
+    std::vector<Batch> batches;
+    for (size_t c = 0; c < n_chunks; c++) {
+        long long p = chunk_first[c];
+        const long long pe = chunk_first[c + 1];
+        while (p < pe) {
             const unsigned long long lim = base[p] + (unsigned long long)cap;
             // largest q with base[q] <= lim
-            q = (long long)(std::upper_bound(base + p, base + pairs + 1, lim) - base) - 1;
+            long long q = (long long)(std::upper_bound(base + p, base + pe + 1, lim) - base) - 1;
             if (q <= p) q = p + 1;
-            batches.emplace_back(p, q);
+            batches.push_back({p, q, c, q == pe});
             p = q;
         }
     }
     long long max_tracks = 0;
-    for (auto &b : batches) max_tracks = std::max(max_tracks, (b.second - b.first) * (long long)h->Z);
-    int rc = ensure_record_capacity(h, std::max<long long>(need, 1), std::max<long long>(max_tracks, 1));
-    if (rc) return rc;
+    for (auto &b : batches) max_tracks = std::max(max_tracks, (b.end - b.first) * (long long)h->Z);
+    if ((rc = ensure_record_capacity(h, std::max<long long>(need, 1), std::max<long long>(max_tracks, 1)))) return rc;
     w = walk_params(h);   // record pointers may have changed
 
     AttenuateParams a;
@@ -831,36 +906,65 @@ extern "C" int moc_sweep(moc_handle *h, long *segments_processed)
         a.inv_2dz2 = 1.0f / (2.f * dz * dz);
     }
 
-    float fill_ms = 0.f, att_ms = 0.f;
-    cudaEvent_t b0 = h->ev[4], b1 = h->ev[5], b2 = h->ev[6];
-    for (auto &b : batches) {
+    // three events per batch: before the fill, between fill and attenuation, after
+    std::vector<cudaEvent_t> ev_b(3 * batches.size());
+    for (auto &e : ev_b)
+        if ((rc = event_at(h, ev_next++, &e))) return rc;
+    size_t chunk_start_batch = 0;
+    for (size_t bi = 0; bi < batches.size(); bi++) {
+        const Batch &b = batches[bi];
+        if (io && (bi == 0 || batches[bi - 1].chunk != b.chunk)) {
+            CUDA_TRY(cudaStreamWaitEvent(h->stream, ev_up[b.chunk], 0));   // this chunk's flux has arrived
+            chunk_start_batch = bi;
+        }
         w.first_pair = b.first;
         w.batch_first_record = base[b.first];
-        CUDA_TRY(cudaEventRecord(b0, h->stream));
-        launch_walk<true>(h, w, b.second - b.first);
+        CUDA_TRY(cudaEventRecord(ev_b[3 * bi], h->stream));
+        launch_walk<true>(h, w, b.end - b.first);
         launches++;
-        CUDA_TRY(cudaEventRecord(b1, h->stream));
+        CUDA_TRY(cudaEventRecord(ev_b[3 * bi + 1], h->stream));
         a.first_track = b.first * h->Z;
-        a.end_track = b.second * h->Z;
+        a.end_track = b.end * h->Z;
         if ((rc = launch_attenuate(h, a, a.end_track - a.first_track))) return rc;
         launches++;
-        CUDA_TRY(cudaEventRecord(b2, h->stream));
-        if (batches.size() > 1) {
-            // per-batch times need the events before they are re-recorded
-            CUDA_TRY(cudaEventSynchronize(b2));
-            float f = 0, t = 0;
-            cudaEventElapsedTime(&f, b0, b1);
-            cudaEventElapsedTime(&t, b1, b2);
-            fill_ms += f;
-            att_ms += t;
+        CUDA_TRY(cudaEventRecord(ev_b[3 * bi + 2], h->stream));
+        if (io && b.last_of_chunk) {
+            // the finished chunk goes home while the next one is swept
+            const size_t t0 = (size_t)batches[chunk_start_batch].first * h->Z, t1 = (size_t)b.end * h->Z;
+            CUDA_TRY(cudaStreamWaitEvent(h->down_stream, ev_b[3 * bi + 2], 0));
+            const int threads = 256;
+            patch_tracks_kernel<<<(unsigned)((t1 - t0 + threads - 1) / threads), threads, 0, h->down_stream>>>(
+                h->d.track_image + t0, (long long)(t1 - t0), h->d.z_height + t0);
+            h->launch_count++;
+            launches++;
+            CUDA_TRY(cudaMemcpyAsync((void *)(io->tracks + t0), h->d.track_image + t0, sizeof(TrackImage) * (t1 - t0),
+                                     cudaMemcpyDeviceToHost, h->down_stream));
+            CUDA_TRY(cudaMemcpy2DAsync(io->psi + 2 * t0 * G, sizeof(float) * 2 * G, h->d.psi + 2 * t0 * G,
+                                       sizeof(float) * 2 * G, sizeof(float) * G, t1 - t0, cudaMemcpyDeviceToHost,
+                                       h->down_stream));
         }
+    }
+    if (io) {
+        // scalar flux (the only part of the source slab the sweep writes), then join the streams
+        const size_t NF = (size_t)h->N * h->F;
+        if (batches.empty()) CUDA_TRY(cudaStreamWaitEvent(h->down_stream, e_scan, 0));
+        CUDA_TRY(cudaMemcpy2DAsync(io->src + NF * G, sizeof(float) * G, h->d.src + NF * h->Gp, sizeof(float) * h->Gp,
+                                   sizeof(float) * G, NF, cudaMemcpyDeviceToHost, h->down_stream));
+        cudaEvent_t e_home;
+        if ((rc = event_at(h, ev_next++, &e_home))) return rc;
+        CUDA_TRY(cudaEventRecord(e_home, h->down_stream));
+        CUDA_TRY(cudaStreamWaitEvent(h->stream, e_home, 0));
     }
     CUDA_TRY(cudaEventRecord(e_end, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     CUDA_TRY(cudaGetLastError());
-    if (batches.size() == 1) {
-        cudaEventElapsedTime(&fill_ms, b0, b1);
-        cudaEventElapsedTime(&att_ms, b1, b2);
+    float fill_ms = 0.f, att_ms = 0.f;
+    for (size_t bi = 0; bi < batches.size(); bi++) {
+        float f = 0, t = 0;
+        cudaEventElapsedTime(&f, ev_b[3 * bi], ev_b[3 * bi + 1]);
+        cudaEventElapsedTime(&t, ev_b[3 * bi + 1], ev_b[3 * bi + 2]);
+        fill_ms += f;
+        att_ms += t;
     }
     cudaEventElapsedTime(&h->timing.count_ms, e_start, e_count);
     cudaEventElapsedTime(&h->timing.scan_ms, e_count, e_scan);
@@ -873,6 +977,15 @@ extern "C" int moc_sweep(moc_handle *h, long *segments_processed)
     h->rand_base += total;   // the serial rand() stream moves on by one draw per segment (solver.c:481)
     if (segments_processed) *segments_processed = (long)total;
     return MOC_OK;
+}
+
+extern "C" int moc_sweep(moc_handle *h, long *segments_processed)
+{
+    if (!h) {
+        moc_set_error("moc_sweep: null handle");
+        return MOC_EINVAL;
+    }
+    return sweep_core(h, segments_processed, nullptr);
 }
 
 extern "C" int moc_get_sweep_timing(moc_handle *h, moc_sweep_timing *t)
@@ -1335,6 +1448,7 @@ struct Mirror {
     moc_handle *h = nullptr;
     bool dirty_sweep = false;   // device holds newer psi/z/flux than the host
     bool dirty_all = false;     // device holds newer everything
+    std::vector<void *> registered;   // host slabs this library page-locked (cudaHostRegister)
 };
 static std::mutex g_mirror_mutex;
 static std::unordered_map<const void *, Mirror> g_mirrors;   // keyed by Params.tracks
@@ -1362,6 +1476,33 @@ extern "C" void moc_dropin_configure(unsigned long long seed, unsigned long long
     g_dropin_source_stride = source_stride;
 }
 
+// The reference allocates its slabs with malloc (tracks.c:87-115, source.c:121).  Asynchronous
+// copies that overlap kernels need page-locked memory, so slabs that are not already pinned
+// (moc_host_alloc pins) are registered in place, once per mirror; failure is not an error -- the
+// copies then simply run synchronously.  MOC_B200_NO_PIN=1 disables it.
+static void pin_range(Mirror &m, const void *p, size_t bytes)
+{
+    if (!p || !bytes) return;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return;
+    }
+    if (at.type != cudaMemoryTypeUnregistered) return;
+    if (cudaHostRegister((void *)p, bytes, cudaHostRegisterPortable) == cudaSuccess) m.registered.push_back((void *)p);
+    else cudaGetLastError();
+}
+
+static void pin_host_slabs(Mirror &m, const HostLayout &L)
+{
+    const char *off = getenv("MOC_B200_NO_PIN");
+    if (off && off[0] == '1') return;
+    const moc_handle *h = m.h;
+    pin_range(m, L.tracks, sizeof(TrackImage) * (size_t)h->T3);
+    pin_range(m, L.psi, sizeof(float) * 2 * (size_t)h->T3 * (size_t)h->G);
+    pin_range(m, L.src, sizeof(float) * (size_t)(2 * h->F + 1) * (size_t)h->N * (size_t)h->G);
+}
+
 [[noreturn]] static void die(const char *where)
 {
     // the reference has no error returns on this path: it prints and exits (solver.c:506-511)
@@ -1372,7 +1513,7 @@ extern "C" void moc_dropin_configure(unsigned long long seed, unsigned long long
 // Find (or build) the device mirror of a host Params.  Non-resident mode re-uploads the
 // mutable state on every call (host is authoritative); resident mode uploads once.
 static Mirror &mirror_for(const Params *P, const Input *I, HostLayout &L, bool need_backward_psi,
-                          const char *where)
+                          const char *where, bool caller_streams = false)
 {
     std::lock_guard<std::mutex> lock(g_mirror_mutex);
     Mirror &m = g_mirrors[(const void *)P->tracks];
@@ -1388,8 +1529,11 @@ static Mirror &mirror_for(const Params *P, const Input *I, HostLayout &L, bool n
     } else if (inspect_layout(I, P, m.h->source_stride, L)) {
         die(where);
     }
+    if (created) pin_host_slabs(m, L);
     if (created || !g_resident) {
-        if (upload_mutable(m.h, L, created || need_backward_psi)) die(where);
+        // caller_streams: the non-resident transport_sweep moves the mutable state itself, chunk by
+        // chunk, overlapped with the kernels (sweep_core); nothing to upload here
+        if (!(caller_streams && !g_resident) && upload_mutable(m.h, L, created || need_backward_psi)) die(where);
         if (P->leakage)
             cudaMemcpyAsync(m.h->d.leakage, P->leakage, sizeof(float), cudaMemcpyHostToDevice, m.h->stream);
     }
@@ -1399,15 +1543,13 @@ static Mirror &mirror_for(const Params *P, const Input *I, HostLayout &L, bool n
 extern "C" void transport_sweep(Params *params, Input *I)
 {
     HostLayout L;
-    Mirror &m = mirror_for(params, I, L, false, "transport_sweep");
+    Mirror &m = mirror_for(params, I, L, false, "transport_sweep", true);
     long segs = 0;
-    if (moc_sweep(m.h, &segs)) die("transport_sweep");
+    // non-resident: uploads, kernels and downloads are pipelined inside the sweep; the call
+    // returns after the last byte is back in the host structures
+    if (sweep_core(m.h, &segs, g_resident ? nullptr : &L)) die("transport_sweep");
     I->segments_processed = segs;
-    if (g_resident) {
-        m.dirty_sweep = true;
-    } else if (download_into(m.h, L, params, 1)) {
-        die("transport_sweep");
-    }
+    if (g_resident) m.dirty_sweep = true;
 }
 
 extern "C" void renormalize_flux(Params params, Input I, CommGrid grid)
@@ -1482,6 +1624,7 @@ extern "C" int moc_release(Params *params)
     auto it = g_mirrors.find((const void *)params->tracks);
     if (it == g_mirrors.end()) return MOC_OK;
     moc_destroy(it->second.h);
+    for (void *p : it->second.registered) cudaHostUnregister(p);
     g_mirrors.erase(it);
     return MOC_OK;
 }

@@ -156,6 +156,19 @@ def test_dropin_names_on_the_reference_own_structures(built):
     for name in ("fine_flux", "psi", "fine_source"):
         a, b = getattr(mine, name), getattr(theirs, name)
         assert rel_l2(a, b) <= TOL, name
+    # the non-resident sweep pipelines copies and kernels per chunk of z-stacks: any chunking and
+    # any staging-buffer size must give the same rays, the same segments, the same flux
+    mirror = L.moc_handle_of(C.byref(params))
+    for chunks, batch in ((3, 0), (7, 20000), (1, 0)):
+        assert L.moc_set_option(mirror, api.OPT_STREAM_CHUNKS, chunks) == 0
+        assert L.moc_set_option(mirror, api.OPT_BATCH_SEGMENTS, batch) == 0
+        L.transport_sweep(C.byref(params), C.byref(inp))
+        assert inp.segments_processed == theirs.sweep()
+        assert np.array_equal(mine.z_height, theirs.z_height)
+        for name in ("fine_flux", "psi"):
+            a, b = getattr(mine, name), getattr(theirs, name)
+            assert rel_l2(a, b) <= TOL, (name, chunks, batch)
+    assert L.moc_set_option(mirror, api.OPT_BATCH_SEGMENTS, 0) == 0
     # resident mode: nothing comes back until moc_sync_to_host
     L.moc_set_resident(1)
     before = mine.fine_flux.copy()
