@@ -201,8 +201,10 @@ enum {
     MOC_OPT_BATCH_SEGMENTS = 4, /* max 3D segments staged per batch (scratch size), default 2^28 */
     MOC_OPT_SOURCE_STRIDE = 5,  /* sizeof(Source) of the caller: 48 (default) or 56 (OPENMP)     */
     MOC_OPT_LANES_PER_TRACK = 6,/* override the lane mapping of the attenuation kernel (0=auto)  */
-    MOC_OPT_STREAM_CHUNKS = 7   /* z-stack chunks the host-side transport_sweep moves the angular
+    MOC_OPT_STREAM_CHUNKS = 7,  /* z-stack chunks the host-side transport_sweep moves the angular
                                    flux in (copies overlap kernels), default 16                  */
+    MOC_OPT_WALK_KERNEL = 8     /* axial ray trace: 0 = auto, 1 = one CTA per z-stack, 2 = one
+                                   warp per z-stack (needs z_stacked <= 128)                     */
 };
 
 /* arrays for moc_get_array / moc_set_array (flat, the reference's slab order) */

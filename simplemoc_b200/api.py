@@ -76,7 +76,9 @@ class SweepTiming(C.Structure):
 # option / array ids (include/moc_b200.h)
 OPT_EXP_MODE, OPT_SEED, OPT_RAND_BASE, OPT_BATCH_SEGMENTS, OPT_SOURCE_STRIDE, OPT_LANES = 1, 2, 3, 4, 5, 6
 OPT_STREAM_CHUNKS = 7
+OPT_WALK_KERNEL = 8
 OPT_DIGEST = 100
+OPT_EXACT_RAY_TRACE = 102
 EXP_TABLE_REF, EXP_SFU = 0, 1
 ARR_FINE_SOURCE, ARR_FINE_FLUX, ARR_SIGT, ARR_PSI, ARR_Z_HEIGHT, ARR_P_WEIGHT, ARR_SEG_COUNT, ARR_QSR_DIGEST = \
     1, 2, 3, 4, 5, 6, 7, 8

@@ -138,6 +138,13 @@ struct moc_handle {
     int source_stride = 48;
     int lanes_override = 0;
     int fast_cell_ok = 0;          // table_cell_check_kernel found no mismatch (see moc_kernels.cuh)
+    unsigned int mod_magic = 0, mod_shift = 0;
+    int mod_fast = 0;              // fastmod_check_kernel found no mismatch (moc_walk_warp.cuh)
+    float max_seg_len = 0.f;
+    unsigned int walk_flags_host = 0;
+    int iv_fast = 0, fine_fast = 0;   // interval_check_kernel found no mismatch (moc_walk_warp.cuh)
+    float iv_lo = 0.f, iv_hi = 0.f;
+    int walk_kernel = 0;           // 0 = auto, 1 = one CTA per z-stack, 2 = one warp per z-stack (Z <= 128)
     int want_digest = 0;
     // scratch capacity
     long long rec_capacity = 0, off_capacity = 0;
@@ -297,6 +304,10 @@ static int upload_static(moc_handle *h, const Params *P, const HostLayout &L)
     }
     start[(size_t)T2] = total;
     h->S2 = total;
+    h->max_seg_len = 0.f;
+    for (long long i = 0; i < T2; i++)
+        for (int n = 0; n < ns[(size_t)i]; n++)
+            h->max_seg_len = std::max(h->max_seg_len, P->tracks_2D[i].segments[n].length);
     std::vector<float> len((size_t)std::max<long long>(total, 1));
     for (long long i = 0; i < T2; i++)
         for (int n = 0; n < ns[(size_t)i]; n++)
@@ -360,6 +371,68 @@ static int upload_static(moc_handle *h, const Params *P, const HostLayout &L)
         cudaFree(bad);
         h->fast_cell_ok = (bad_host == 0 && x_max > 0.f);
     }
+    // May the ray-trace kernel reduce rand() draws modulo n_regions with a multiplication?  Only if
+    // it agrees with the hardware remainder for every possible draw (all 2^31 of them).
+    h->mod_fast = 0;
+    if (h->N > 1 && h->N < (1ll << 24)) {
+        const uint32_t n = (uint32_t)h->N;
+        uint32_t L = 0;
+        while ((1ull << L) < n) L++;
+        const unsigned long long magic = ((1ull << (31 + L)) / n) + 1ull;
+        if (magic <= 0xffffffffull && L >= 1) {
+            unsigned long long *bad = nullptr, bad_host = 1;
+            CUDA_TRY(cudaMalloc((void **)&bad, sizeof(unsigned long long)));
+            CUDA_TRY(cudaMemset(bad, 0, sizeof(unsigned long long)));
+            fastmod_check_kernel<<<148 * 16, 256>>>(n, (uint32_t)magic, L - 1, bad);
+            CUDA_TRY(cudaMemcpy(&bad_host, bad, sizeof bad_host, cudaMemcpyDeviceToHost));
+            cudaFree(bad);
+            if (bad_host == 0) {
+                h->mod_magic = (uint32_t)magic;
+                h->mod_shift = L - 1;
+                h->mod_fast = 1;
+            }
+        }
+    }
+    return MOC_OK;
+}
+
+static WalkParams walk_params(const moc_handle *h);
+
+// May the ray trace compute fine intervals with the FMA quotient (moc_walk_warp.cuh)?  Only if it
+// returns the integer of the IEEE division for every float a ray height can take: checked
+// exhaustively over [-node_dz, 2 node_dz] (~3e9 floats, a few ms), once per handle.
+static int verify_fast_intervals(moc_handle *h)
+{
+    const WalkParams w = walk_params(h);
+    h->iv_fast = h->fine_fast = 0;
+    const float hi = 2.0f * (float)w.node_dz, lo = -(float)w.node_dz;
+    if (!(hi > 0.f) || !(w.dz_interval > 0.f) || !(w.dz_fine > 0.f)) return MOC_OK;
+    if ((double)hi / (double)w.dz_interval >= 4194304.0 || (double)hi / (double)w.dz_fine >= 4194304.0) return MOC_OK;
+    unsigned int bits_hi, bits_lo;
+    memcpy(&bits_hi, &hi, 4);
+    memcpy(&bits_lo, &lo, 4);
+    unsigned long long *bad = nullptr, bad_host[3] = {1, 1, 1};
+    CUDA_TRY(cudaMalloc((void **)&bad, 3 * sizeof(unsigned long long)));
+    CUDA_TRY(cudaMemset(bad, 0, 3 * sizeof(unsigned long long)));
+    const int grid = 148 * 16;
+    interval_check_kernel<<<grid, 256>>>(0u, bits_hi, w.dz_interval, 1.0f / w.dz_interval, 0, bad);
+    interval_check_kernel<<<grid, 256>>>(0u, bits_hi, w.dz_interval, 1.0f / w.dz_interval, 1, bad + 1);
+    interval_check_kernel<<<grid, 256>>>(0x80000000u, bits_lo, w.dz_interval, 1.0f / w.dz_interval, 1, bad + 1);
+    interval_check_kernel<<<grid, 256>>>(0u, bits_hi, w.dz_fine, 1.0f / w.dz_fine, 0, bad + 2);
+    CUDA_TRY(cudaMemcpy(bad_host, bad, sizeof bad_host, cudaMemcpyDeviceToHost));
+    cudaFree(bad);
+    // no trial height z + s cos(polar) may leave the verified range: s <= max length / min |sin|
+    double min_sin = 1.0;
+    {
+        std::vector<double> sp((size_t)h->P);
+        cudaMemcpy(sp.data(), h->d.sin_p, sizeof(double) * (size_t)h->P, cudaMemcpyDeviceToHost);
+        for (double v : sp) min_sin = std::min(min_sin, fabs(v));
+    }
+    const bool advance_ok = min_sin > 0.0 && (double)h->max_seg_len / min_sin <= w.node_dz;
+    h->iv_fast = (bad_host[0] == 0 && bad_host[1] == 0 && advance_ok);
+    h->fine_fast = (bad_host[2] == 0);
+    h->iv_lo = lo;
+    h->iv_hi = hi;
     return MOC_OK;
 }
 
@@ -458,6 +531,7 @@ static int create_common(const Input *I, const Params *P, int device, int source
             return fail(MOC_ECUDA);
         }
     if ((rc = upload_static(h, P, L))) return fail(rc);
+    if ((rc = verify_fast_intervals(h))) return fail(rc);
     const size_t T3 = (size_t)h->T3, G = (size_t)h->G, N = (size_t)h->N, F = (size_t)h->F;
     const size_t pairs = (size_t)h->T2 * h->P;
     if ((rc = dev_alloc(&h->d.track_image, T3))) return fail(rc);
@@ -469,7 +543,7 @@ static int create_common(const Input *I, const Params *P, int device, int source
     if ((rc = dev_alloc(&h->d.seg_count, T3))) return fail(rc);
     if ((rc = dev_alloc(&h->d.pair_count, pairs))) return fail(rc);
     if ((rc = dev_alloc(&h->d.pair_base, pairs + 1))) return fail(rc);
-    if ((rc = dev_alloc(&h->d.digest, 4))) return fail(rc);
+    if ((rc = dev_alloc(&h->d.digest, 5))) return fail(rc);   // [4]: ray-trace flags
     if ((rc = dev_alloc(&h->d.per_region_a, N))) return fail(rc);
     if ((rc = dev_alloc(&h->d.per_region_b, N))) return fail(rc);
     if ((rc = dev_alloc(&h->d.per_fine, N * F))) return fail(rc);
@@ -480,7 +554,7 @@ static int create_common(const Input *I, const Params *P, int device, int source
         return fail(MOC_ENOMEM);
     }
     cudaMemsetAsync(h->d.seg_count, 0, sizeof(uint32_t) * T3, h->stream);
-    cudaMemsetAsync(h->d.digest, 0, sizeof(unsigned long long) * 4, h->stream);
+    cudaMemsetAsync(h->d.digest, 0, sizeof(unsigned long long) * 5, h->stream);
     cudaMemsetAsync(h->d.scalars, 0, sizeof(float) * 8, h->stream);
     h->leakage_host = P->leakage ? *P->leakage : 0.f;
     cudaMemcpyAsync(h->d.leakage, &h->leakage_host, sizeof(float), cudaMemcpyHostToDevice, h->stream);
@@ -529,11 +603,18 @@ extern "C" int moc_set_option(moc_handle *h, int option, long value)
         if (value != 0 && value != 4 && value != 8 && value != 16 && value != 32) break;
         h->lanes_override = (int)value;
         return MOC_OK;
+    case MOC_OPT_WALK_KERNEL:
+        if (value < 0 || value > 2) break;
+        h->walk_kernel = (int)value;
+        return MOC_OK;
     case MOC_OPT_STREAM_CHUNKS:
         if (value < 1 || value > 4096) break;
         h->stream_chunks = (int)value;
         return MOC_OK;
     case 100: h->want_digest = value != 0; return MOC_OK;   // MOC_OPT_DIGEST (diagnostic)
+    case 102:                                                // diagnostic: 1 = ray trace with IEEE divisions / hardware remainders only
+        if (value) h->iv_fast = h->fine_fast = h->mod_fast = 0;
+        return MOC_OK;
     case 101:                                                // MOC_OPT_EXACT_DIV (diagnostic): 1 = never use the fast cell selection
         if (value) h->fast_cell_ok = 0;
         return MOC_OK;
@@ -553,8 +634,10 @@ extern "C" long moc_get_option(moc_handle *h, int option)
     case MOC_OPT_SOURCE_STRIDE: return h->source_stride;
     case MOC_OPT_LANES_PER_TRACK: return h->lanes_override;
     case MOC_OPT_STREAM_CHUNKS: return h->stream_chunks;
+    case MOC_OPT_WALK_KERNEL: return h->walk_kernel;
     case 100: return h->want_digest;
     case 101: return !h->fast_cell_ok;
+    case 102: return !(h->iv_fast && h->fine_fast && h->mod_fast);
     }
     return -1;
 }
@@ -585,6 +668,10 @@ static WalkParams walk_params(const moc_handle *h)
     w.fai = h->F;
     w.axial_exp = I.axial_exp;
     w.n_regions = (unsigned int)h->N;
+    w.mod_magic = h->mod_magic;
+    w.mod_shift = h->mod_shift;
+    w.mod_fast = h->mod_fast;
+    w.fai_magic = (unsigned int)((1ull << 32) / (unsigned long long)std::max(h->F, 1)) + 1u;
     w.z_sep = I.axial_z_sep;
     // solver.c:288-289: float / int, widened; then double / int
     const double node_dz = (double)(float)(I.height / I.decomp_assemblies_ax);
@@ -594,6 +681,14 @@ static WalkParams walk_params(const moc_handle *h)
     w.dz_interval = (float)fine_dz;
     // solver.c:38: float / int
     w.dz_fine = I.height / (I.fai * I.decomp_assemblies_ax * I.cai);
+    w.node_dz_f = (float)node_dz;
+    w.flags = reinterpret_cast<unsigned int *>(h->d.digest + 4);
+    w.iv_fast = h->iv_fast;
+    w.fine_fast = h->fine_fast;
+    w.iv_lo = h->iv_lo;
+    w.iv_hi = h->iv_hi;
+    w.iv_rdz = 1.0f / w.dz_interval;
+    w.fine_rdz = 1.0f / w.dz_fine;
     w.seed = h->seed;
     w.rand_base = h->rand_base;
     return w;
@@ -604,6 +699,27 @@ static void launch_walk(const moc_handle *h, const WalkParams &w, long long n_pa
 {
     if (n_pairs <= 0) return;
     const int Z = h->Z;
+    if (h->walk_kernel != 1 && Z <= 128) {
+        // short stacks: one warp per stack, 4 stacks per CTA, one launch per ray direction
+        const long long P = h->P, H = P / 2, p0 = w.first_pair, p1 = w.first_pair + n_pairs;
+        auto ups_before = [&](long long p) { return (p / P) * H + std::min<long long>(p % P, H); };
+        const long long up0 = ups_before(p0), n_up = ups_before(p1) - up0;
+        const long long down0 = p0 - up0, n_down = n_pairs - n_up;
+        const int kpt = (Z + 31) / 32;
+        const bool fast = h->iv_fast && h->fine_fast;
+#define MOC_WALK(K, UP, before, n)                                                                                \
+    if (kpt == K && (n) > 0) {                                                                                    \
+        const unsigned grid = (unsigned)(((n) + 3) / 4);                                                          \
+        if (fast) stack_walk_warp_kernel<K, FILL, UP, true><<<grid, 128, 0, h->stream>>>(w, before, n);           \
+        else stack_walk_warp_kernel<K, FILL, UP, false><<<grid, 128, 0, h->stream>>>(w, before, n);               \
+        h->launch_count++;                                                                                        \
+    }
+        MOC_WALK(1, true, up0, n_up) MOC_WALK(2, true, up0, n_up) MOC_WALK(3, true, up0, n_up) MOC_WALK(4, true, up0, n_up)
+        MOC_WALK(1, false, down0, n_down) MOC_WALK(2, false, down0, n_down) MOC_WALK(3, false, down0, n_down)
+        MOC_WALK(4, false, down0, n_down)
+#undef MOC_WALK
+        return;
+    }
     int kpt = 1;
     while (kpt < 16 && (Z + kpt - 1) / kpt > 256) kpt *= 2;
     int threads = ((Z + kpt - 1) / kpt + 31) / 32 * 32;
@@ -765,7 +881,7 @@ static int sweep_core(moc_handle *h, long *segments_processed, const HostLayout 
     const long long pairs = h->T2 * h->P;
     const size_t G = (size_t)h->G;
     cudaEvent_t e_start = h->ev[0], e_count = h->ev[1], e_scan = h->ev[2], e_end = h->ev[3];
-    long launches = 0;
+    const long launches_before = h->launch_count;
     int rc;
 
     // ---- chunks of whole z-stacks (only the host-streamed sweep has more than one)
@@ -808,18 +924,27 @@ static int sweep_core(moc_handle *h, long *segments_processed, const HostLayout 
         unpack_tracks_kernel<<<(unsigned)((h->T3 + threads - 1) / threads), threads, 0, h->stream>>>(
             h->d.track_image, h->T3, h->d.p_weight, h->d.z_height);
         h->launch_count++;
-        launches++;
     }
 
     // ---- pass 1: segment counts per ray and per (2D track, polar angle) stack
     WalkParams w = walk_params(h);
     if (h->want_digest) cudaMemsetAsync(h->d.digest, 0, sizeof(unsigned long long) * 4, h->stream);
     launch_walk<false>(h, w, pairs);
-    launches++;
+    if (h->iv_fast && h->fine_fast) {
+        // a ray height outside the node (never produced by the sweep itself, but the host may hand us
+        // anything) voids the range the fast interval arithmetic was verified on: count again exactly
+        CUDA_TRY(cudaMemcpyAsync(&h->walk_flags_host, w.flags, sizeof(unsigned int), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+        if (h->walk_flags_host) {
+            h->iv_fast = h->fine_fast = 0;
+            cudaMemsetAsync(w.flags, 0, sizeof(unsigned int), h->stream);
+            w = walk_params(h);
+            launch_walk<false>(h, w, pairs);
+        }
+    }
     CUDA_TRY(cudaEventRecord(e_count, h->stream));
     pair_scan_kernel<<<1, 1024, 0, h->stream>>>(h->d.pair_count, h->d.pair_base, pairs);
     h->launch_count++;
-    launches++;
     CUDA_TRY(cudaMemcpyAsync(h->pair_base_pinned, h->d.pair_base, sizeof(unsigned long long) * (size_t)(pairs + 1),
                              cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(cudaEventRecord(e_scan, h->stream));
@@ -921,12 +1046,10 @@ static int sweep_core(moc_handle *h, long *segments_processed, const HostLayout 
         w.batch_first_record = base[b.first];
         CUDA_TRY(cudaEventRecord(ev_b[3 * bi], h->stream));
         launch_walk<true>(h, w, b.end - b.first);
-        launches++;
         CUDA_TRY(cudaEventRecord(ev_b[3 * bi + 1], h->stream));
         a.first_track = b.first * h->Z;
         a.end_track = b.end * h->Z;
         if ((rc = launch_attenuate(h, a, a.end_track - a.first_track))) return rc;
-        launches++;
         CUDA_TRY(cudaEventRecord(ev_b[3 * bi + 2], h->stream));
         if (io && b.last_of_chunk) {
             // the finished chunk goes home while the next one is swept
@@ -936,8 +1059,7 @@ static int sweep_core(moc_handle *h, long *segments_processed, const HostLayout 
             patch_tracks_kernel<<<(unsigned)((t1 - t0 + threads - 1) / threads), threads, 0, h->down_stream>>>(
                 h->d.track_image + t0, (long long)(t1 - t0), h->d.z_height + t0);
             h->launch_count++;
-            launches++;
-            CUDA_TRY(cudaMemcpyAsync((void *)(io->tracks + t0), h->d.track_image + t0, sizeof(TrackImage) * (t1 - t0),
+                CUDA_TRY(cudaMemcpyAsync((void *)(io->tracks + t0), h->d.track_image + t0, sizeof(TrackImage) * (t1 - t0),
                                      cudaMemcpyDeviceToHost, h->down_stream));
             CUDA_TRY(cudaMemcpy2DAsync(io->psi + 2 * t0 * G, sizeof(float) * 2 * G, h->d.psi + 2 * t0 * G,
                                        sizeof(float) * 2 * G, sizeof(float) * G, t1 - t0, cudaMemcpyDeviceToHost,
@@ -972,7 +1094,7 @@ static int sweep_core(moc_handle *h, long *segments_processed, const HostLayout 
     h->timing.fill_ms = fill_ms;
     h->timing.attenuate_ms = att_ms;
     h->timing.n_batches = (long)batches.size();
-    h->timing.launches = launches;
+    h->timing.launches = h->launch_count - launches_before;
     h->I.segments_processed = (long)total;
     h->rand_base += total;   // the serial rand() stream moves on by one draw per segment (solver.c:481)
     if (segments_processed) *segments_processed = (long)total;

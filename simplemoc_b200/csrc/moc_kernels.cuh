@@ -59,6 +59,14 @@ struct WalkParams {
     long long first_pair;             // first (i*P+j) of this launch
     int P, Z, fai, axial_exp;
     unsigned int n_regions;
+    // x % n_regions and x % fai by multiplication (moc_walk_warp.cuh); mod_fast = 0: hardware remainder
+    unsigned int mod_magic, mod_shift, fai_magic;
+    int mod_fast;
+    // fine intervals without the division sequence (moc_walk_warp.cuh): valid for z in [iv_lo, iv_hi]
+    int iv_fast, fine_fast;           // verified for dz_interval (both roundings) / for dz_fine (truncation)
+    float iv_rdz, fine_rdz, iv_lo, iv_hi;
+    float node_dz_f;                  // node_dz is a float value widened (solver.c:288)
+    unsigned int *flags;              // bit 0: a ray height outside [0, node_dz] met the fast intervals
     float z_sep;                      // axial_z_sep
     float dz_interval;                // (float)fine_delta_z : what get_*_interval receive
     double fine_dz, node_dz;          // solver.c:288-289
@@ -389,6 +397,8 @@ __global__ void stack_walk_kernel(const WalkParams w)
         if (threadIdx.x == 0) w.pair_count[pair] = tot;
     }
 }
+
+#include "moc_walk_warp.cuh"
 
 // exclusive scan of pair_count[n] into pair_base[n+1]; single CTA (n ~ 2e5).
 __global__ void pair_scan_kernel(const unsigned long long *in, unsigned long long *out, long long n)

@@ -64,6 +64,10 @@ CASES = {
     "odd": [3, 3, 3, 4, 2, 2.5, 5.0, 6, 3, 10, 0, 1, 8, 21.42, 400.0, 0.01, 96, 0],
     # G=100 / 20 segments per track as in the shipped default.in, scaled down
     "mini_default_in": [17, 17, 9, 5, 2, 2.0, 0.25, 8, 10, 100, 1, 20, 20, 21.42, 400.0, 0.01, 80, 0],
+    # z-stacks of 25 rays (one ray per lane of the warp-per-stack ray trace) and of 200 rays
+    # (more than a warp can own: the CTA-per-stack ray trace)
+    "short": [3, 3, 4, 3, 2, 2.0, 16.0, 8, 4, 16, 0, 1, 10, 21.42, 400.0, 0.01, 200, 0],
+    "tall": [3, 3, 4, 3, 2, 4.0, 2.0, 8, 4, 16, 0, 1, 10, 21.42, 400.0, 0.01, 200, 0],
     # 96 000 short 3D tracks, G=8: large enough for one 10 000-track message per face
     # (comms.c:12-28), cheap to sweep -- the boundary-exchange case
     "exch": [3, 3, 4, 3, 2, 2.0, 0.05, 8, 4, 8, 1, 20, 10, 21.42, 400.0, 0.01, 200, 0],

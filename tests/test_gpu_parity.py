@@ -15,7 +15,7 @@ TOL = 1e-4          # north_star: scalar flux and k-eff within 1e-4 relative (FP
 FRAC = 0.999
 
 
-def make_pair(case, seed, exp_mode=0, batch=0, lanes=0):
+def make_pair(case, seed, exp_mode=0, batch=0, lanes=0, walk=0, exact=False):
     vals = CASES[case]
     host = m.HostProblem(m.derive(m.input_from_values(vals)), seed=seed)
     dev = m.DeviceProblem(host, device=0, exp_mode=exp_mode)
@@ -24,6 +24,10 @@ def make_pair(case, seed, exp_mode=0, batch=0, lanes=0):
         dev.set_option(api.OPT_BATCH_SEGMENTS, batch)
     if lanes:
         dev.set_option(api.OPT_LANES, lanes)
+    if walk:
+        dev.set_option(api.OPT_WALK_KERNEL, walk)
+    if exact:
+        dev.set_option(api.OPT_EXACT_RAY_TRACE, 1)   # IEEE divisions and hardware remainders only
     oracle = OracleCase(vals, seed=seed, exp_mode=exp_mode)
     return host, dev, oracle
 
@@ -100,6 +104,28 @@ def test_batching_is_invisible(built, batch):
     assert np.array_equal(dev.get(api.ARR_SEG_COUNT), oracle.seg_count)
     assert np.array_equal(dev.get(api.ARR_QSR_DIGEST), oracle.digest)
     check_state(dev, oracle, f"batch={batch}")
+    dev.close(); host.close(); oracle.close()
+
+
+@pytest.mark.parametrize("case,walk,exact", [("short", 0, False), ("short", 1, False), ("tiny", 1, False),
+                                             ("odd", 1, False), ("mini104", 1, False), ("mini104", 2, False),
+                                             ("tall", 0, False), ("tiny_flat", 1, False), ("tiny", 2, True),
+                                             ("mini104", 0, True), ("short", 0, True), ("odd", 0, True)])
+def test_ray_trace_kernels_agree(built, case, walk, exact):
+    """K0 has two mappings (one warp per z-stack for Z <= 128, one CTA per z-stack otherwise;
+    walk = 0 picks by Z) and the warp mapping two arithmetic variants (verified FMA intervals /
+    IEEE divisions): all must reproduce the oracle's integers exactly, over two sweeps."""
+    host, dev, oracle = make_pair(case, seed=4, walk=walk, exact=exact)
+    if exact or case in ("short", "tiny", "tiny_flat", "odd"):
+        # geometries whose 2D segments are short against the node height qualify for the verified
+        # FMA intervals (moc_create checks); the others keep the IEEE divisions by themselves
+        assert dev.get_option(api.OPT_EXACT_RAY_TRACE) == (1 if exact else 0)
+    for sweep in range(2):
+        assert dev.sweep() == oracle.sweep()
+        assert np.array_equal(dev.get(api.ARR_SEG_COUNT), oracle.seg_count)
+        assert np.array_equal(dev.get(api.ARR_QSR_DIGEST), oracle.digest)
+        assert np.array_equal(dev.get(api.ARR_Z_HEIGHT), oracle.z_height)
+        check_state(dev, oracle, f"{case} walk={walk} sweep {sweep}", frac_floor=0.99)
     dev.close(); host.close(); oracle.close()
 
 
