@@ -73,13 +73,28 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0,
                     help="target CPU time of the cpu_baseline sample")
+    ap.add_argument("--egroups", type=int, default=0,
+                    help="override n_egroups (BASELINE config 4: 32 / 64 / 128 on the default geometry)")
+    ap.add_argument("--decomp-ax", type=int, default=0,
+                    help="override decomp_assemblies_ax (BASELINE config 5: 2 = ~131 GB per GPU)")
     ap.add_argument("--grid", default="", help="cx,cy,cz (default: 1x1x1, 2x1x1, 2x2x1, 2x2x2)")
     return ap.parse_args()
 
 
 # ------------------------------------------------------------------ helpers
 
-def workload_input(m, name):
+def workload_input(m, name, egroups=0, decomp_ax=0):
+    inp, label = _workload_input(m, name)
+    if egroups:
+        inp.n_egroups = egroups
+        label += f"; n_egroups overridden to {egroups}"
+    if decomp_ax:
+        inp.decomp_assemblies_ax = decomp_ax
+        label += f"; decomp_assemblies_ax overridden to {decomp_ax}"
+    return inp, label
+
+
+def _workload_input(m, name):
     if name == "default":
         inp = m.default_input()
         label = ("default strawman problem, built-in set_default_input (src/init.c:33-74): "
@@ -269,7 +284,7 @@ def run_reference(args):
     per_step = max(2.0, min(20.0, 150.0 / (args.steps + args.warmup)))
     value, sec_per_step, desc = time_reference(args, args.steps, args.warmup, per_step)
     import simplemoc_b200 as m
-    _, label = workload_input(m, args.workload)
+    _, label = workload_input(m, args.workload)     # the reference arm runs the named workload as shipped
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * sec_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -307,7 +322,7 @@ def run_moc(args):
         if dist is not None:
             dist.barrier()
 
-    inp, label = workload_input(m, args.workload)
+    inp, label = workload_input(m, args.workload, args.egroups, args.decomp_ax)
     inp.mype = rank
     inp = m.derive(inp, args.limit_tracks_2d)
     t0 = time.time()
@@ -330,9 +345,8 @@ def run_moc(args):
     state = {"keff": 1.0, "segments": 0, "att_ms": 0.0, "fill_ms": 0.0, "count_ms": 0.0, "sweep_ms": 0.0}
 
     def step(accumulate):
-        n = dev.sweep()
-        if world > 1:
-            dev.exchange(grid)
+        # N > 1: the exchange runs under the sweep of the interior z-stacks (moc_sweep_exchange)
+        n = dev.sweep_exchange(grid) if world > 1 else dev.sweep()
         dev.renormalize()
         # main.c:81,89 feeds each iteration's k-eff to the next update_sources.  With neighbours the
         # reference adds UN-normalised boundary flux sums to the leakage (comms.c:120) and never
@@ -402,6 +416,19 @@ def run_moc(args):
             "l2": {"achieved_gbs": my_integ * L2_BYTES_PER_INTEGRATION / att_s / 1e9 if att_s else None,
                    "bytes_per_integration": L2_BYTES_PER_INTEGRATION},
             "note": "not HBM-bound: FP32 issue + L2 gather/atomic bound (DESIGN.md 'roofline')"}
+    # the measured ceiling of the kernel's memory side: the same gathers + vector reductions on the
+    # same (L2-resident) slab without the arithmetic, timed live (moc_probe_l2_gather)
+    try:
+        if inp.fai >= 3 and inp.axial_exp == 2:
+            probe_mix, probe_rd = dev.probe_l2_gather(1), dev.probe_l2_gather(0)
+            G4 = (G // 32) * 32 if G >= 32 else G     # the probe moves whole 128-byte quads
+            iface = my_integ * 20.0 / att_s / 1e9 if att_s else None   # 16 B gathered + 4 B reduced per integration
+            roof["l2"].update({"sm_l2_interface_bytes_per_integration": 20, "achieved_interface_gbs": iface,
+                               "probe_gather_gbs": probe_rd / 1e9, "probe_gather_plus_red_gbs": probe_mix / 1e9,
+                               "frac_of_probe": iface / (probe_mix / 1e9) if iface else None,
+                               "probe": "moc_probe_l2_gather: K1's access pattern on the same slab, no arithmetic"})
+    except Exception as e:   # diagnostics only
+        roof["l2"]["probe_error"] = str(e)
     roof["frac"] = roof["achieved"] / hbm_peak if roof["achieved"] else None
 
     cpu = None
@@ -418,7 +445,7 @@ def run_moc(args):
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": label, "domains": f"{cx}x{cy}x{cz}", "exp": args.exp,
-                           "step": "transport_sweep" + (" + boundary exchange" if world > 1 else "") +
+                           "step": "transport_sweep" + (" + boundary exchange (overlapped)" if world > 1 else "") +
                                    " + renormalize_flux + update_sources + compute_keff",
                            "ntracks_per_gpu": T3, "n_egroups": G,
                            "segments_per_sweep_per_gpu": state["segments"] // n_launch,

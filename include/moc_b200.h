@@ -241,6 +241,11 @@ int moc_renormalize(moc_handle *h);                            /* renormalize_fl
 int moc_update_sources(moc_handle *h, float keff, float *res); /* update_sources    */
 int moc_compute_keff(moc_handle *h, float *keff);              /* compute_keff      */
 int moc_exchange(moc_handle *h, const CommGrid *grid);         /* fast_transfer_... */
+/* transport_sweep + fast_transfer_boundary_fluxes (main.c:60-70) as one call: the exchange starts
+ * as soon as the z-stacks whose flux it moves (the first tracks of the slab, comms.c:100-183) are
+ * swept and runs on a second stream under the sweep of the remaining stacks.  Same results as
+ * moc_sweep followed by moc_exchange. */
+int moc_sweep_exchange(moc_handle *h, const CommGrid *grid, long *segments_processed);
 
 int moc_get_sweep_timing(moc_handle *h, moc_sweep_timing *t);
 int moc_get_array(moc_handle *h, int which, void *dst, size_t bytes);
@@ -251,6 +256,10 @@ float moc_get_leakage(moc_handle *h);
 int moc_synchronize(moc_handle *h);
 /* the cudaStream_t every kernel of this handle is launched on (for CUDA-event timing by the caller) */
 void *moc_get_stream(moc_handle *h);
+/* diagnostics: bytes/s the L2 delivers for the attenuation kernel's access pattern on this
+ * handle's source slab without the arithmetic (mode 0: row gathers, 1: gathers + vector
+ * reductions) -- the measured ceiling bench.py reports the kernel's L2-level rate against */
+int moc_probe_l2_gather(moc_handle *h, int mode, double *bytes_per_second);
 /* kernels launched through this handle since moc_create (the library counts its own launches) */
 long moc_get_launch_count(moc_handle *h);
 

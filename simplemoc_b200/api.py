@@ -92,9 +92,9 @@ EXPORTED = [
     "fast_transfer_boundary_fluxes", "moc_dropin_configure", "moc_set_device", "moc_handle_of",
     "moc_set_resident", "moc_sync_to_host", "moc_release",
     "moc_create", "moc_destroy", "moc_set_option", "moc_get_option", "moc_sweep",
-    "moc_renormalize", "moc_update_sources", "moc_compute_keff", "moc_exchange",
+    "moc_renormalize", "moc_update_sources", "moc_compute_keff", "moc_exchange", "moc_sweep_exchange",
     "moc_get_sweep_timing", "moc_get_array", "moc_set_array", "moc_download", "moc_upload",
-    "moc_get_leakage", "moc_synchronize", "moc_get_stream", "moc_get_launch_count", "moc_comm_get_unique_id", "moc_comm_init",
+    "moc_get_leakage", "moc_synchronize", "moc_get_stream", "moc_get_launch_count", "moc_probe_l2_gather", "moc_comm_get_unique_id", "moc_comm_init",
     "moc_make_grid", "moc_exchange_plan", "moc_last_error", "moc_device_count", "moc_set_default_input",
     "moc_set_small_input", "moc_read_input_file", "moc_read_CLI",
     "moc_calculate_derived_inputs", "moc_est_mem_usage", "moc_build_tracks",
@@ -141,6 +141,7 @@ def lib():
     L.moc_update_sources.argtypes = [vp, C.c_float, C.POINTER(C.c_float)]
     L.moc_compute_keff.argtypes = [vp, C.POINTER(C.c_float)]
     L.moc_exchange.argtypes = [vp, C.POINTER(CommGrid)]
+    L.moc_sweep_exchange.argtypes = [vp, C.POINTER(CommGrid), lp]
     L.moc_get_sweep_timing.argtypes = [vp, C.POINTER(SweepTiming)]
     L.moc_get_array.argtypes = [vp, C.c_int, vp, C.c_size_t]
     L.moc_set_array.argtypes = [vp, C.c_int, vp, C.c_size_t]
@@ -153,6 +154,7 @@ def lib():
     L.moc_get_stream.argtypes = [vp]
     L.moc_get_launch_count.restype = C.c_long
     L.moc_get_launch_count.argtypes = [vp]
+    L.moc_probe_l2_gather.argtypes = [vp, C.c_int, C.POINTER(C.c_double)]
     L.moc_comm_get_unique_id.argtypes = [C.c_char_p]
     L.moc_comm_init.argtypes = [vp, C.c_int, C.c_int, C.c_char_p]
     L.moc_make_grid.argtypes = [C.c_int] * 4 + [C.POINTER(CommGrid)]
@@ -329,6 +331,18 @@ class DeviceProblem:
 
     def exchange(self, grid):
         _check(lib().moc_exchange(self.h, C.byref(grid)), "moc_exchange")
+
+    def probe_l2_gather(self, mode):
+        """bytes/s of the attenuation kernel's gather (+ reduction) pattern alone (diagnostic)"""
+        v = C.c_double(0)
+        _check(lib().moc_probe_l2_gather(self.h, mode, C.byref(v)), "moc_probe_l2_gather")
+        return v.value
+
+    def sweep_exchange(self, grid):
+        """sweep + boundary exchange, the exchange overlapped with the interior stacks"""
+        n = C.c_long(0)
+        _check(lib().moc_sweep_exchange(self.h, C.byref(grid), C.byref(n)), "moc_sweep_exchange")
+        return n.value
 
     def comm_init(self, nranks, rank, unique_id):
         _check(lib().moc_comm_init(self.h, nranks, rank, unique_id), "moc_comm_init")

@@ -161,6 +161,9 @@ struct moc_handle {
     long long *exch_table = nullptr;
     float *exch_sums = nullptr;
     long exch_capacity = 0;
+    CommGrid exch_grid;
+    long exch_table_ops = 0;
+    bool exch_table_ready = false;
     cudaStream_t comm_stream = nullptr;
 };
 
@@ -857,6 +860,8 @@ static int ensure_record_capacity(moc_handle *h, long long records, long long tr
     return MOC_OK;
 }
 
+static int exchange_on_stream(moc_handle *h, const CommGrid *grid, cudaStream_t st);   // comms section
+
 // events of the per-batch pipeline, created on demand and kept for the next sweep
 static int event_at(moc_handle *h, size_t idx, cudaEvent_t *out)
 {
@@ -875,7 +880,12 @@ static int event_at(moc_handle *h, size_t idx, cudaEvent_t *out)
 // travels in `stream_chunks` chunks of whole z-stacks on a copy stream while earlier
 // chunks are swept, and every finished chunk (flux rows, ray heights) goes back on a
 // third stream -- host<->device copies overlap the kernels in both directions.
-static int sweep_core(moc_handle *h, long *segments_processed, const HostLayout *io)
+//
+// overlap_grid != nullptr (resident problem only): the boundary exchange of comms.c is started on a
+// second stream as soon as the z-stacks whose angular flux it moves -- the first tracks of the
+// slab, comms.c:100-183 -- have been swept, and runs under the sweep of the interior stacks.
+static int sweep_core(moc_handle *h, long *segments_processed, const HostLayout *io,
+                      const CommGrid *overlap_grid = nullptr)
 {
     CUDA_TRY(cudaSetDevice(h->device));
     const long long pairs = h->T2 * h->P;
@@ -886,12 +896,23 @@ static int sweep_core(moc_handle *h, long *segments_processed, const HostLayout 
 
     // ---- chunks of whole z-stacks (only the host-streamed sweep has more than one)
     std::vector<long long> chunk_first;   // first pair of every chunk, plus the end
-    {
+    long long boundary_pairs = 0;         // z-stacks that hold the flux the boundary exchange moves
+    if (overlap_grid && !io) {
+        const long n_ops = moc_exchange_plan(&h->I, overlap_grid, nullptr, 0);
+        if (n_ops < 0) return (int)n_ops;
+        const long long floats = (long long)n_ops * 10000ll * h->G;              // comms.c:12-28: whole messages
+        const long long tracks = (floats + 2ll * h->G - 1) / (2ll * h->G);       // [t][2][G] slab
+        boundary_pairs = std::min<long long>((tracks + h->Z - 1) / h->Z, pairs);
+    }
+    if (boundary_pairs > 0 && boundary_pairs < pairs) {
+        chunk_first = {0, boundary_pairs, pairs};
+    } else {
         long long n = io ? std::min<long long>(std::max(h->stream_chunks, 1), std::max<long long>(pairs, 1)) : 1;
         const long long per = (pairs + n - 1) / std::max<long long>(n, 1);
         for (long long p = 0; p < pairs; p += std::max<long long>(per, 1)) chunk_first.push_back(p);
         chunk_first.push_back(pairs);
     }
+    cudaEvent_t e_exchanged = nullptr;    // recorded on the communication stream after the exchange
     const size_t n_chunks = chunk_first.size() - 1;
     size_t ev_next = 0;
     std::vector<cudaEvent_t> ev_up(n_chunks);
@@ -1051,6 +1072,15 @@ static int sweep_core(moc_handle *h, long *segments_processed, const HostLayout 
         a.end_track = b.end * h->Z;
         if ((rc = launch_attenuate(h, a, a.end_track - a.first_track))) return rc;
         CUDA_TRY(cudaEventRecord(ev_b[3 * bi + 2], h->stream));
+        if (overlap_grid && !io && b.last_of_chunk && b.end == std::max<long long>(boundary_pairs, 1) &&
+            (boundary_pairs < pairs || bi + 1 == batches.size()) && !e_exchanged) {
+            // every track the exchange touches has its outgoing flux: exchange under the interior sweep
+            if (!h->comm_stream) CUDA_TRY(cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking));
+            CUDA_TRY(cudaStreamWaitEvent(h->comm_stream, ev_b[3 * bi + 2], 0));
+            if ((rc = exchange_on_stream(h, overlap_grid, h->comm_stream))) return rc;
+            if ((rc = event_at(h, ev_next++, &e_exchanged))) return rc;
+            CUDA_TRY(cudaEventRecord(e_exchanged, h->comm_stream));
+        }
         if (io && b.last_of_chunk) {
             // the finished chunk goes home while the next one is swept
             const size_t t0 = (size_t)batches[chunk_start_batch].first * h->Z, t1 = (size_t)b.end * h->Z;
@@ -1076,6 +1106,14 @@ static int sweep_core(moc_handle *h, long *segments_processed, const HostLayout 
         if ((rc = event_at(h, ev_next++, &e_home))) return rc;
         CUDA_TRY(cudaEventRecord(e_home, h->down_stream));
         CUDA_TRY(cudaStreamWaitEvent(h->stream, e_home, 0));
+    }
+    if (overlap_grid && !io) {
+        if (!e_exchanged) {
+            // no interior to hide behind (the exchange covers every stack, or there are none)
+            if ((rc = exchange_on_stream(h, overlap_grid, h->stream))) return rc;
+        } else {
+            CUDA_TRY(cudaStreamWaitEvent(h->stream, e_exchanged, 0));
+        }
     }
     CUDA_TRY(cudaEventRecord(e_end, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
@@ -1114,6 +1152,56 @@ extern "C" int moc_get_sweep_timing(moc_handle *h, moc_sweep_timing *t)
 {
     if (!h || !t) return MOC_EINVAL;
     *t = h->timing;
+    return MOC_OK;
+}
+
+extern "C" int moc_sweep_exchange(moc_handle *h, const CommGrid *grid, long *segments_processed)
+{
+    if (!h || !grid) {
+        moc_set_error("moc_sweep_exchange: null argument");
+        return MOC_EINVAL;
+    }
+    return sweep_core(h, segments_processed, nullptr, grid);
+}
+
+// Measured ceiling of the attenuation kernel's memory side: the same gathers (3 source rows + sigT,
+// 128 bytes per 8 lanes) and vector reductions on the handle's own source slab, no arithmetic.
+// mode 0: gathers only, 1: gathers + reductions.  The flux slab receives zeros only.
+extern "C" int moc_probe_l2_gather(moc_handle *h, int mode, double *bytes_per_second)
+{
+    if (!h || !bytes_per_second || h->F < 3) {
+        moc_set_error("moc_probe_l2_gather: needs a handle with fai >= 3");
+        return MOC_EINVAL;
+    }
+    CUDA_TRY(cudaSetDevice(h->device));
+    const int quads = h->G / 32 > 0 ? h->G / 32 : 1, pitch4 = h->Gp / 4, iters = 2000;
+    int sm = 0;
+    CUDA_TRY(cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, h->device));
+    const unsigned blocks = (unsigned)sm * 5 * 4;
+    float4 *sink = nullptr, *zeros = nullptr;
+    const size_t slab_rows = (size_t)h->N * h->F;
+    CUDA_TRY(cudaMalloc((void **)&sink, 64));
+    // reductions go to a scratch copy of the flux slab so the problem state is untouched
+    CUDA_TRY(cudaMalloc((void **)&zeros, slab_rows * h->Gp * sizeof(float)));
+    CUDA_TRY(cudaMemsetAsync(zeros, 0, slab_rows * h->Gp * sizeof(float), h->stream));
+    const float4 *src = reinterpret_cast<const float4 *>(h->d.src);
+    float ms = 0.f;
+    for (int pass = 0; pass < 2; pass++) {   // first pass warms the L2
+        CUDA_TRY(cudaEventRecord(h->ev[6], h->stream));
+        if (mode == 0)
+            l2_gather_probe_kernel<false><<<blocks, 128, 0, h->stream>>>(src, zeros, (uint32_t)h->N, (uint32_t)h->F, pitch4, quads, iters, sink);
+        else
+            l2_gather_probe_kernel<true><<<blocks, 128, 0, h->stream>>>(src, zeros, (uint32_t)h->N, (uint32_t)h->F, pitch4, quads, iters, sink);
+        CUDA_TRY(cudaEventRecord(h->ev[7], h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+        CUDA_TRY(cudaGetLastError());
+        cudaEventElapsedTime(&ms, h->ev[6], h->ev[7]);
+    }
+    cudaFree(sink);
+    cudaFree(zeros);
+    const double segs = (double)blocks * 16.0 * iters;
+    const double bytes = segs * quads * 128.0 * (mode == 0 ? 4.0 : 5.0);
+    *bytes_per_second = bytes / ((double)ms * 1e-3);
     return MOC_OK;
 }
 
@@ -1477,6 +1565,7 @@ static int exchange_on_stream(moc_handle *h, const CommGrid *grid, cudaStream_t 
         h->exch_table = nullptr;
         h->exch_sums = nullptr;
         CUDA_TRY(cudaMalloc((void **)&h->exch_table, sizeof(long long) * 3 * (size_t)n_ops));
+        h->exch_table_ready = false;
         CUDA_TRY(cudaMalloc((void **)&h->exch_sums, sizeof(float) * (size_t)n_ops));
         h->exch_capacity = n_ops;
     }
@@ -1486,9 +1575,15 @@ static int exchange_on_stream(moc_handle *h, const CommGrid *grid, cudaStream_t 
         CUDA_TRY(cudaMalloc((void **)&h->recv_stage, sizeof(float) * (size_t)n_recv * (size_t)chunk));
         h->stage_chunks = n_recv;
     }
-    // pageable source: the copy is staged by the runtime before the call returns
-    CUDA_TRY(cudaMemcpyAsync(h->exch_table, tab.data(), sizeof(long long) * 3 * (size_t)n_ops,
-                             cudaMemcpyHostToDevice, st));
+    // The tables depend on the grid only: upload once.  (A pageable cudaMemcpyAsync synchronises the
+    // host with the stream first -- the overlapped form must not wait for the boundary sweep here.)
+    if (!h->exch_table_ready || memcmp(&h->exch_grid, grid, sizeof(CommGrid)) != 0 || h->exch_table_ops != n_ops) {
+        CUDA_TRY(cudaStreamSynchronize(st));
+        CUDA_TRY(cudaMemcpy(h->exch_table, tab.data(), sizeof(long long) * 3 * (size_t)n_ops, cudaMemcpyHostToDevice));
+        h->exch_grid = *grid;
+        h->exch_table_ops = n_ops;
+        h->exch_table_ready = true;
+    }
     // 1) leakage of the border faces, in the reference's accumulation order
     if (n_border > 0) {
         border_chunk_sums_kernel<<<(unsigned)n_border, 256, 0, st>>>(h->d.psi, h->exch_table + 2 * n_ops, chunk,

@@ -676,4 +676,47 @@ __global__ void exchange_scatter_kernel(float4 *slab, const float4 *stage, const
     }
 }
 
+
+// ------------------------------------------------------------------ diagnostics: L2 gather probe
+
+// What the L2 delivers for the access pattern of attenuate_kernel, without its arithmetic: groups
+// of 8 lanes read 128 contiguous bytes per quad from 3 consecutive pseudo-random source rows and
+// the region's sigT row, and (RED) reduce one float4 per lane into the flux slab.  bench.py
+// reports the attenuation kernel's L2-level rate against this measured ceiling.
+__device__ __forceinline__ uint32_t probe_hash(uint32_t x)
+{
+    x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+    return x;
+}
+
+template <bool RED>
+__global__ void __launch_bounds__(128) l2_gather_probe_kernel(const float4 *__restrict__ src, float4 *flux,
+                                                              uint32_t n_regions, uint32_t fai, int pitch4, int quads,
+                                                              int iters, float4 *sink)
+{
+    const int lane8 = threadIdx.x & 7;
+    const uint32_t track = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    float4 acc = make_float4(0, 0, 0, 0);
+    const float4 *sig = src + (size_t)2 * n_regions * fai * pitch4;
+    for (int it = 0; it < iters; it++) {
+        const uint32_t h = probe_hash(track * 0x9E3779B9u + it);
+        const uint32_t region = h % n_regions;
+        const uint32_t r0 = (h >> 24) % (fai - 2);
+        const float4 *row = src + ((size_t)region * fai + r0) * pitch4;
+        for (int v = 0; v < quads; v++) {
+            float4 t = make_float4(0, 0, 0, 0);
+#pragma unroll
+            for (int r = 0; r < 3; r++) {
+                const float4 y = __ldg(row + r * pitch4 + lane8 + 8 * v);
+                t.x += y.x; t.y += y.y; t.z += y.z; t.w += y.w;
+            }
+            const float4 s4 = __ldg(sig + (size_t)region * pitch4 + lane8 + 8 * v);
+            t.x += s4.x; t.y += s4.y; t.z += s4.z; t.w += s4.w;
+            if (RED) red_add_v4(reinterpret_cast<float *>(flux + ((size_t)region * fai + r0 + 1) * pitch4 + lane8 + 8 * v), t);
+            acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+        }
+    }
+    if (acc.x == 123.456f) sink[0] = acc;
+}
+
 }  // namespace moc

@@ -71,6 +71,24 @@ def main():
     assert abs(k - k_model) <= 1e-4 * abs(k_model), (k, k_model)
     print(f"rank {rank}/{world}: exchange bit-exact, leakage {dev.leakage:.6g}, keff {k:.6f} (model {k_model:.6f}), ok",
           flush=True)
+    # the overlapped form (moc_sweep_exchange) against the two separate calls, from the same host data
+    def fresh():
+        d = m.DeviceProblem(host, device=local)
+        b2 = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            b2.copy_(torch.frombuffer(bytearray(api.nccl_unique_id()), dtype=torch.uint8))
+        dist.broadcast(b2, 0)
+        d.comm_init(world, rank, bytes(b2.cpu().numpy().tobytes()))
+        return d
+    one, two = fresh(), fresh()
+    grid = m.make_grid(cx, cy, cz, rank)
+    n1 = one.sweep()
+    one.exchange(grid)
+    n2 = two.sweep_exchange(grid)
+    assert n1 == n2
+    assert np.array_equal(one.get(api.ARR_PSI), two.get(api.ARR_PSI)), f"rank {rank}: overlapped exchange differs"
+    assert one.leakage == two.leakage
+    one.close(); two.close()
     dist.barrier()
     dev.close(); host.close()
     dist.destroy_process_group()

@@ -39,6 +39,30 @@ def test_single_domain_every_face_leaks(built):
     dev.close(); host.close(); oracle.close()
 
 
+def test_overlapped_sweep_exchange_equals_two_calls(built):
+    """moc_sweep_exchange starts the exchange once the boundary stacks are swept and runs it under
+    the interior stacks on a second stream: same slab, same leakage, same ray state as
+    moc_sweep followed by moc_exchange -- over two iterations."""
+    vals = CASES["exch"]
+    host = m.HostProblem(m.derive(m.input_from_values(vals)), seed=8)
+    a, b = m.DeviceProblem(host, device=0), m.DeviceProblem(host, device=0)
+    grid = m.make_grid(1, 1, 1, 0)
+    for it in range(2):
+        na = a.sweep()
+        a.exchange(grid)
+        nb = b.sweep_exchange(grid)
+        assert na == nb
+        assert b.timing().n_batches >= 2              # boundary stacks, then interior stacks
+        assert np.array_equal(a.get(api.ARR_PSI), b.get(api.ARR_PSI)), it
+        assert np.array_equal(a.get(api.ARR_Z_HEIGHT), b.get(api.ARR_Z_HEIGHT))
+        assert a.leakage == b.leakage and a.leakage != 0
+        # the scalar flux is accumulated with floating-point atomics (order varies run to run):
+        # continue both from the same tallies so the next iteration is comparable bit for bit
+        b.set(api.ARR_FINE_FLUX, a.get(api.ARR_FINE_FLUX))
+        a.renormalize(); b.renormalize()
+    a.close(); b.close(); host.close()
+
+
 def test_exchange_needs_a_communicator(built):
     host = m.HostProblem(m.derive(m.input_from_values(CASES["exch"])), seed=6)
     dev = m.DeviceProblem(host, device=0)

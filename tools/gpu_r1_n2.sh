@@ -1,0 +1,6 @@
+set -x
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=index,name --format=csv,noheader
+python -m pytest tests -m gpu -q -k "exchange" 2>&1 | tail -8 | tee gpurun_out/pytest_gpu_n2.log
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 3 --warmup 3 > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err
+tail -c 2500 gpurun_out/bench_n2.json; tail -5 gpurun_out/bench_n2.err
