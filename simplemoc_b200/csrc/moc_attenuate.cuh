@@ -226,8 +226,8 @@ __global__ void __launch_bounds__(128, MOC_ATT_MIN_BLOCKS) attenuate_kernel(cons
     float mu = 0.f;
     if (valid) {
         n_rec = a.seg_count[t];
-        at = a.track_off[t - a.first_track];
         const long long pair = t / a.Z;
+        at = (uint32_t)(a.rec_base[pair] - a.batch_first_record) + (uint32_t)(t - pair * a.Z);
         const int j = (int)(pair % a.P);
         const long long i = pair / a.P;
         mu = a.mu[j];
@@ -261,18 +261,20 @@ __global__ void __launch_bounds__(128, MOC_ATT_MIN_BLOCKS) attenuate_kernel(cons
         psi1[s] = (valid && g < G) ? psi_row[g] : 0.f;
     }
 
-    // Segment records: the L lanes of a track fetch L consecutive records with one coalesced load
-    // (lane `lit` holds record block*L + lit) one block ahead of use; each segment's record is then
-    // broadcast from its holder with a width-L shuffle.
+    // Segment records: the L lanes of a track fetch its next L records (lane `lit` holds record
+    // block*L + lit) one block ahead of use; each segment's record is then broadcast from its holder
+    // with a width-L shuffle.  Records are segment-major inside a z-stack (record j of ray k at
+    // base + j*Zs + k), so the tracks of a warp/CTA -- neighbouring rays -- share 32-byte sectors.
     const float *rec_ds = a.rec_ds + at;
     const float *rec_zin = a.rec_zin + at;
     const uint32_t *rec_code = a.rec_code + at;
     float cur_ds = 0.f, cur_zin = 0.f, nxt_ds = 0.f, nxt_zin = 0.f;
     uint32_t cur_code = 0, nxt_code = 0;
+    const uint32_t Zs = (uint32_t)a.Zs;   // the j-th record of a track is Zs words after its (j-1)-th
     if ((uint32_t)lit < n_rec) {
-        nxt_ds = __ldg(rec_ds + lit);
-        nxt_zin = __ldg(rec_zin + lit);
-        nxt_code = __ldg(rec_code + lit);
+        nxt_ds = __ldg(rec_ds + lit * Zs);
+        nxt_zin = __ldg(rec_zin + lit * Zs);
+        nxt_code = __ldg(rec_code + lit * Zs);
     }
     const float *const src_q = a.fine_source + 4 * lit;          // this lane's quads
     const float *const sig_q = a.sigT + 4 * lit;
@@ -287,9 +289,9 @@ __global__ void __launch_bounds__(128, MOC_ATT_MIN_BLOCKS) attenuate_kernel(cons
             cur_ds = nxt_ds; cur_zin = nxt_zin; cur_code = nxt_code;
             const uint32_t ahead = sgm + L + lit;
             if (ahead < n_rec) {
-                nxt_ds = __ldg(rec_ds + ahead);
-                nxt_zin = __ldg(rec_zin + ahead);
-                nxt_code = __ldg(rec_code + ahead);
+                nxt_ds = __ldg(rec_ds + ahead * Zs);
+                nxt_zin = __ldg(rec_zin + ahead * Zs);
+                nxt_code = __ldg(rec_code + ahead * Zs);
             }
         }
         const float seg_ds = __shfl_sync(0xffffffffu, cur_ds, slot, L);

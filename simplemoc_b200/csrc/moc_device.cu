@@ -9,8 +9,9 @@
  *   xs         float [X][G][3],  scatter float [X][G][G],  xs_index int [N],  vol float [N]
  *   tracks     SoA: p_weight[T3], z_height[T3] (unpacked on the device from the 40-byte AoS)
  *   2D tracks  SoA: az_weight[T2], n_seg[T2], seg_start[T2+1], seg_len[S2]
- *   sweep scratch: seg_count u32[T3], pair_count/pair_base u64[T2*P(+1)], and per batch
- *                  track_off u32[tracks], rec_ds f32[], rec_zin f32[], rec_code u32[]
+ *   sweep scratch: seg_count u32[T3], pair_count/pair_base/rec_base u64[T2*P(+1)], pair_max u32[T2*P],
+ *                  and per batch the segment records rec_ds f32[], rec_zin f32[], rec_code u32[]
+ *                  (segment-major inside a z-stack: record j of ray k at rec_base[stack] + j*Zs + k)
  *
  * There is no CPU implementation behind any entry point: without a usable CUDA device
  * every compute call fails with MOC_ENODEVICE.
@@ -107,8 +108,8 @@ struct DeviceBuffers {
     float *src = nullptr, *xs = nullptr, *scatter = nullptr, *vol = nullptr, *table = nullptr;
     int *xs_index = nullptr;
     // sweep scratch
-    uint32_t *seg_count = nullptr, *track_off = nullptr, *rec_code = nullptr;
-    unsigned long long *pair_count = nullptr, *pair_base = nullptr, *digest = nullptr;
+    uint32_t *seg_count = nullptr, *pair_max = nullptr, *rec_code = nullptr;
+    unsigned long long *pair_count = nullptr, *pair_base = nullptr, *rec_base = nullptr, *digest = nullptr;
     float *rec_ds = nullptr, *rec_zin = nullptr;
     // reductions
     float *per_region_a = nullptr, *per_region_b = nullptr, *per_fine = nullptr, *scalars = nullptr;
@@ -147,7 +148,7 @@ struct moc_handle {
     int walk_kernel = 0;           // 0 = auto, 1 = one CTA per z-stack, 2 = one warp per z-stack (Z <= 128)
     int want_digest = 0;
     // scratch capacity
-    long long rec_capacity = 0, off_capacity = 0;
+    long long rec_capacity = 0;
     std::vector<unsigned long long> pair_base_host;
     unsigned long long *pair_base_pinned = nullptr;
     moc_sweep_timing timing;
@@ -192,7 +193,7 @@ static void free_buffers(DeviceBuffers &d)
 {
     void *all[] = {d.az_weight, d.n_seg, d.seg_start, d.seg_len, d.cos_p, d.sin_p, d.mu, d.p_weight,
                    d.z_height, d.psi, d.track_image, d.src, d.xs, d.scatter, d.vol, d.table,
-                   d.xs_index, d.seg_count, d.track_off, d.rec_code, d.pair_count, d.pair_base,
+                   d.xs_index, d.seg_count, d.pair_max, d.rec_code, d.pair_count, d.pair_base, d.rec_base,
                    d.digest, d.rec_ds, d.rec_zin, d.per_region_a, d.per_region_b, d.per_fine,
                    d.scalars, d.leakage};
     for (void *p : all)
@@ -546,13 +547,15 @@ static int create_common(const Input *I, const Params *P, int device, int source
     if ((rc = dev_alloc(&h->d.seg_count, T3))) return fail(rc);
     if ((rc = dev_alloc(&h->d.pair_count, pairs))) return fail(rc);
     if ((rc = dev_alloc(&h->d.pair_base, pairs + 1))) return fail(rc);
+    if ((rc = dev_alloc(&h->d.rec_base, pairs + 1))) return fail(rc);
+    if ((rc = dev_alloc(&h->d.pair_max, pairs))) return fail(rc);
     if ((rc = dev_alloc(&h->d.digest, 5))) return fail(rc);   // [4]: ray-trace flags
     if ((rc = dev_alloc(&h->d.per_region_a, N))) return fail(rc);
     if ((rc = dev_alloc(&h->d.per_region_b, N))) return fail(rc);
     if ((rc = dev_alloc(&h->d.per_fine, N * F))) return fail(rc);
     if ((rc = dev_alloc(&h->d.scalars, 8))) return fail(rc);
     if ((rc = dev_alloc(&h->d.leakage, 1))) return fail(rc);
-    if (cudaHostAlloc((void **)&h->pair_base_pinned, sizeof(unsigned long long) * (pairs + 1), cudaHostAllocDefault) != cudaSuccess) {
+    if (cudaHostAlloc((void **)&h->pair_base_pinned, sizeof(unsigned long long) * 2 * (pairs + 1), cudaHostAllocDefault) != cudaSuccess) {
         moc_set_error("cudaHostAlloc(pair_base) failed");
         return fail(MOC_ENOMEM);
     }
@@ -661,10 +664,12 @@ static WalkParams walk_params(const moc_handle *h)
     w.seg_count = h->d.seg_count;
     w.pair_count = h->d.pair_count;
     w.pair_base = h->d.pair_base;
+    w.rec_base = h->d.rec_base;
+    w.pair_max = h->d.pair_max;
+    w.Zs = (h->Z + 7) / 8 * 8;
     w.rec_ds = h->d.rec_ds;
     w.rec_zin = h->d.rec_zin;
     w.rec_code = h->d.rec_code;
-    w.track_off = h->d.track_off;
     w.digest = h->want_digest ? h->d.digest : nullptr;
     w.P = h->P;
     w.Z = h->Z;
@@ -834,7 +839,7 @@ static int launch_attenuate(const moc_handle *h, const AttenuateParams &a, long 
     return MOC_EINVAL;
 }
 
-static int ensure_record_capacity(moc_handle *h, long long records, long long tracks)
+static int ensure_record_capacity(moc_handle *h, long long records)
 {
     if (records > h->rec_capacity) {
         if (h->d.rec_ds) cudaFree(h->d.rec_ds);
@@ -848,14 +853,6 @@ static int ensure_record_capacity(moc_handle *h, long long records, long long tr
         if ((rc = dev_alloc(&h->d.rec_zin, (size_t)records))) return rc;
         if ((rc = dev_alloc(&h->d.rec_code, (size_t)records))) return rc;
         h->rec_capacity = records;
-    }
-    if (tracks > h->off_capacity) {
-        if (h->d.track_off) cudaFree(h->d.track_off);
-        h->d.track_off = nullptr;
-        h->off_capacity = 0;
-        int rc;
-        if ((rc = dev_alloc(&h->d.track_off, (size_t)tracks))) return rc;
-        h->off_capacity = tracks;
     }
     return MOC_OK;
 }
@@ -950,6 +947,7 @@ static int sweep_core(moc_handle *h, long *segments_processed, const HostLayout 
     // ---- pass 1: segment counts per ray and per (2D track, polar angle) stack
     WalkParams w = walk_params(h);
     if (h->want_digest) cudaMemsetAsync(h->d.digest, 0, sizeof(unsigned long long) * 4, h->stream);
+    CUDA_TRY(cudaMemsetAsync(h->d.pair_max, 0, sizeof(unsigned int) * (size_t)std::max<long long>(pairs, 1), h->stream));
     launch_walk<false>(h, w, pairs);
     if (h->iv_fast && h->fine_fast) {
         // a ray height outside the node (never produced by the sweep itself, but the host may hand us
@@ -964,15 +962,19 @@ static int sweep_core(moc_handle *h, long *segments_processed, const HostLayout 
         }
     }
     CUDA_TRY(cudaEventRecord(e_count, h->stream));
-    pair_scan_kernel<<<1, 1024, 0, h->stream>>>(h->d.pair_count, h->d.pair_base, pairs);
+    pair_scan_kernel<<<1, 1024, 0, h->stream>>>(h->d.pair_count, h->d.pair_max, w.Zs, h->d.pair_base, h->d.rec_base, pairs);
     h->launch_count++;
     CUDA_TRY(cudaMemcpyAsync(h->pair_base_pinned, h->d.pair_base, sizeof(unsigned long long) * (size_t)(pairs + 1),
+                             cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(h->pair_base_pinned + pairs + 1, h->d.rec_base, sizeof(unsigned long long) * (size_t)(pairs + 1),
                              cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(cudaEventRecord(e_scan, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     CUDA_TRY(cudaGetLastError());
-    const unsigned long long *base = h->pair_base_pinned;
-    const unsigned long long total = base[pairs];
+    // base[]: record slots (segment-major stacks: Zs * longest ray each) -- what the staging buffers
+    // and the batches are sized by; the segment total is the last entry of the serial scan
+    const unsigned long long *base = h->pair_base_pinned + pairs + 1;
+    const unsigned long long total = h->pair_base_pinned[pairs];
 
     // ---- batches of whole stacks whose records fit the staging buffers (never across a chunk)
     unsigned long long largest_pair = 0, largest_chunk = 0;
@@ -980,12 +982,12 @@ static int sweep_core(moc_handle *h, long *segments_processed, const HostLayout 
     for (size_t c = 0; c < n_chunks; c++)
         largest_chunk = std::max(largest_chunk, base[chunk_first[c + 1]] - base[chunk_first[c]]);
     if (largest_pair >= (1ull << 32)) {
-        moc_set_error("a single z-stack produces %llu segments (> 2^32)", largest_pair);
+        moc_set_error("a single z-stack needs %llu record slots (> 2^32)", largest_pair);
         return MOC_EINVAL;
     }
-    // 2 % headroom: the segment count drifts from sweep to sweep (stale ray heights, solver.c:514-523)
-    // and re-allocating multi-GB staging buffers costs hundreds of milliseconds
-    const unsigned long long want = largest_chunk + largest_chunk / 50 + 1024;
+    // 10 % headroom: the record rows a stack needs (its longest ray) drift from sweep to sweep (stale
+    // ray heights, solver.c:514-523) and re-allocating multi-GB staging buffers costs ~0.2 s
+    const unsigned long long want = largest_chunk + largest_chunk / 10 + 1024;
     long long cap = h->batch_segments;
     if (cap <= 0 && (long long)largest_chunk <= h->rec_capacity) {
         cap = h->rec_capacity;   // the staging buffers of the previous sweep are large enough
@@ -1016,9 +1018,7 @@ static int sweep_core(moc_handle *h, long *segments_processed, const HostLayout 
             p = q;
         }
     }
-    long long max_tracks = 0;
-    for (auto &b : batches) max_tracks = std::max(max_tracks, (b.end - b.first) * (long long)h->Z);
-    if ((rc = ensure_record_capacity(h, std::max<long long>(need, 1), std::max<long long>(max_tracks, 1)))) return rc;
+    if ((rc = ensure_record_capacity(h, std::max<long long>(need, 1)))) return rc;
     w = walk_params(h);   // record pointers may have changed
 
     AttenuateParams a;
@@ -1026,7 +1026,8 @@ static int sweep_core(moc_handle *h, long *segments_processed, const HostLayout 
     a.rec_ds = h->d.rec_ds;
     a.rec_zin = h->d.rec_zin;
     a.rec_code = h->d.rec_code;
-    a.track_off = h->d.track_off;
+    a.rec_base = h->d.rec_base;
+    a.Zs = w.Zs;
     a.seg_count = h->d.seg_count;
     a.p_weight = h->d.p_weight;
     a.az_weight = h->d.az_weight;
@@ -1065,6 +1066,7 @@ static int sweep_core(moc_handle *h, long *segments_processed, const HostLayout 
         }
         w.first_pair = b.first;
         w.batch_first_record = base[b.first];
+        a.batch_first_record = base[b.first];
         CUDA_TRY(cudaEventRecord(ev_b[3 * bi], h->stream));
         launch_walk<true>(h, w, b.end - b.first);
         CUDA_TRY(cudaEventRecord(ev_b[3 * bi + 1], h->stream));

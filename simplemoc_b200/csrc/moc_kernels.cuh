@@ -47,15 +47,17 @@ struct WalkParams {
     // 3D track state
     float *z_height;                  // [T3]  (written by the FILL pass only)
     uint32_t *seg_count;              // [T3]  written by pass 1, read by pass 2
-    unsigned long long *pair_count;   // [T2*P] pass 1 output
-    const unsigned long long *pair_base;  // [T2*P+1] exclusive scan of pair_count
+    unsigned long long *pair_count;   // [T2*P] pass 1 output: 3D segments of the stack
+    unsigned int *pair_max;           // [T2*P] pass 1 output: most 3D segments on one ray of the stack
+    const unsigned long long *pair_base;  // [T2*P+1] exclusive scan of pair_count (serial segment index)
+    const unsigned long long *rec_base;   // [T2*P+1] exclusive scan of Zs * pair_max (record slots)
     // records (pass 2)
     float *rec_ds;
     float *rec_zin;
     uint32_t *rec_code;
-    uint32_t *track_off;              // [tracks in batch] first record, batch-relative
     unsigned long long *digest;       // [4] optional (nullptr = off)
-    unsigned long long batch_first_record;   // pair_base[first pair of the batch]
+    unsigned long long batch_first_record;   // rec_base[first pair of the batch]
+    int Zs;                           // record row pitch of a stack: Z rounded up to 8 (32-byte sectors)
     long long first_pair;             // first (i*P+j) of this launch
     int P, Z, fai, axial_exp;
     unsigned int n_regions;
@@ -78,7 +80,9 @@ struct AttenuateParams {
     const float *rec_ds;
     const float *rec_zin;
     const uint32_t *rec_code;
-    const uint32_t *track_off;        // batch-relative
+    const unsigned long long *rec_base;   // [T2*P+1] first record slot of every stack
+    unsigned long long batch_first_record;
+    int Zs;                           // records of a stack: slot(ray k, segment j) = base + j * Zs + k
     const uint32_t *seg_count;        // [T3]
     const float *p_weight;            // [T3]
     const float *az_weight;           // [T2]
@@ -204,9 +208,10 @@ __device__ __forceinline__ int walk_segment(const WalkParams &w, float &zh, floa
                 else r0 = fine - 1;
                 which = fine - r0;
             }
-            w.rec_ds[slot + made] = ds;
-            w.rec_zin[slot + made] = zin;
-            w.rec_code[slot + made] = pack_code(qsr, (uint32_t)r0, (uint32_t)which);
+            const unsigned long long at = slot + (unsigned long long)made * w.Zs;   // segment-major inside the stack
+            w.rec_ds[at] = ds;
+            w.rec_zin[at] = zin;
+            w.rec_code[at] = pack_code(qsr, (uint32_t)r0, (uint32_t)which);
             if (dg) {
                 const unsigned long long m = serial + (unsigned)made;
                 const unsigned long long row = (unsigned long long)qsr * w.fai + fine;
@@ -261,26 +266,12 @@ __global__ void stack_walk_kernel(const WalkParams w)
 
     unsigned long long serial_at = 0;   // serial index of the first segment of this step
     if (FILL) {
-        // record layout is track-major: offsets = exclusive scan of the pass-1 counts
-        unsigned long long mine = 0;
-        uint32_t c[KPT];
-#pragma unroll
-        for (int r = 0; r < KPT; r++) {
-            c[r] = (k0 + r < w.Z) ? w.seg_count[t0 + k0 + r] : 0u;
-            mine += c[r];
-        }
-        unsigned long long tot;
-        unsigned long long at = block_exclusive_scan(mine, scratch, tot);
+        // records of a stack are segment-major: slot(ray k, its j-th segment) = base + j * Zs + k, so
+        // the rays of a stack write neighbouring words at every step (full 32-byte sectors)
         serial_at = w.pair_base[pair];
-        at += serial_at - w.batch_first_record;
+        const unsigned long long base = w.rec_base[pair] - w.batch_first_record;
 #pragma unroll
-        for (int r = 0; r < KPT; r++) {
-            if (k0 + r < w.Z) {
-                w.track_off[(pair - w.first_pair) * w.Z + k0 + r] = (uint32_t)at;
-                cursor[r] = at;
-            }
-            at += c[r];
-        }
+        for (int r = 0; r < KPT; r++) cursor[r] = base + k0 + r;
     }
 
     int lo = 0, hi = w.Z;
@@ -351,7 +342,7 @@ __global__ void stack_walk_kernel(const WalkParams w)
                                                          cursor[r], w.digest ? dg : nullptr);
                         else walk_segment<false, true>(w, z, home[r], s_full, cos_p, last, left, serial,
                                                        cursor[r], w.digest ? dg : nullptr);
-                        cursor[r] += cnt[r];
+                        cursor[r] += (unsigned long long)cnt[r] * w.Zs;
                     }
                     zh[r] = z_after[r];
                     made_total[r] += cnt[r];
@@ -395,27 +386,39 @@ __global__ void stack_walk_kernel(const WalkParams w)
         unsigned long long tot;
         block_exclusive_scan(mine, scratch, tot);
         if (threadIdx.x == 0) w.pair_count[pair] = tot;
+        // the longest ray decides how many record rows the stack needs
+        uint32_t longest = 0;
+#pragma unroll
+        for (int r = 0; r < KPT; r++) longest = max(longest, made_total[r]);
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) longest = max(longest, __shfl_xor_sync(0xffffffffu, longest, d));
+        if ((threadIdx.x & 31) == 0) atomicMax(w.pair_max + pair, longest);
     }
 }
 
 #include "moc_walk_warp.cuh"
 
-// exclusive scan of pair_count[n] into pair_base[n+1]; single CTA (n ~ 2e5).
-__global__ void pair_scan_kernel(const unsigned long long *in, unsigned long long *out, long long n)
+// exclusive scans over the stacks, single CTA (n ~ 2e5): pair_count -> pair_base (serial segment
+// index of a stack's first segment), Zs * pair_max -> rec_base (its first record slot)
+__global__ void pair_scan_kernel(const unsigned long long *count, const unsigned int *longest, int Zs,
+                                 unsigned long long *serial_base, unsigned long long *rec_base, long long n)
 {
     __shared__ unsigned long long scratch[34];
     const long long per = (n + blockDim.x - 1) / blockDim.x;
     const long long a = (long long)threadIdx.x * per;
     const long long b = (a + per < n) ? a + per : n;
-    unsigned long long mine = 0;
-    for (long long e = a; e < b; e++) mine += in[e];
-    unsigned long long tot;
-    unsigned long long run = block_exclusive_scan(mine, scratch, tot);
-    for (long long e = a; e < b; e++) {
-        out[e] = run;
-        run += in[e];
+    for (int which = 0; which < 2; which++) {
+        unsigned long long mine = 0;
+        for (long long e = a; e < b; e++) mine += which ? (unsigned long long)longest[e] * Zs : count[e];
+        unsigned long long tot;
+        unsigned long long run = block_exclusive_scan(mine, scratch, tot);
+        unsigned long long *out = which ? rec_base : serial_base;
+        for (long long e = a; e < b; e++) {
+            out[e] = run;
+            run += which ? (unsigned long long)longest[e] * Zs : count[e];
+        }
+        if (threadIdx.x == 0) out[n] = tot;
     }
-    if (threadIdx.x == 0) out[n] = tot;
 }
 
 // ------------------------------------------------------------------ K1: attenuation

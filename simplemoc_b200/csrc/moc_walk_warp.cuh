@@ -18,6 +18,8 @@
  *     correctly rounded quotient from a correctly rounded reciprocal (3 DP operations);
  *   - s_full = length / sin(polar) (a double division, uniform over the stack) is evaluated by
  *     lane l for step 32*b + l and broadcast, instead of by every lane for every step;
+ *   - records are segment-major inside a stack (slot(ray k, segment j) = base + j * Zs + k): the
+ *     rays of a stack write neighbouring words at every step instead of one word per 500 bytes;
  *   - the emitting pass walks ONCE: segment length, axial offset and stencil rows are written
  *     while walking (the slot of a segment inside its track is known), the source region -- which
  *     depends on the segment's serial index, i.e. on the scan -- is added afterwards from a byte
@@ -193,23 +195,15 @@ __device__ __forceinline__ void walk_stack_warp(const WalkParams &w, const long 
     if (FAST && !FILL && bad_height) atomicOr(w.flags, 1u);   // the host repeats the sweep with IEEE divisions
 
     unsigned long long serial_at = 0;   // serial index of the first segment of the current step
+    uint32_t base = 0;                  // record slot of (ray 0, segment 0) of this stack, batch-relative
     if (FILL) {
-        // records are track-major: offsets = exclusive scan of the pass-1 counts
-        uint32_t c[KPT], mine = 0;
-#pragma unroll
-        for (int r = 0; r < KPT; r++) {
-            c[r] = (k0 + r < Z) ? w.seg_count[t0 + k0 + r] : 0u;
-            mine += c[r];
-        }
+        // records of a stack are segment-major: slot(ray k, its j-th segment) = base + j * Zs + k, so
+        // the rays of a stack write neighbouring words at every step (full 32-byte sectors);
+        // cursor[r] = j, end[r] = the ray's segment count from pass 1 (rays cut from the window stop there)
         serial_at = w.pair_base[pair];
-        uint32_t at = warp_inclusive_scan_u32(mine, lane) - mine + (uint32_t)(serial_at - w.batch_first_record);
+        base = (uint32_t)(w.rec_base[pair] - w.batch_first_record);
 #pragma unroll
-        for (int r = 0; r < KPT; r++) {
-            if (k0 + r < Z) w.track_off[local * Z + k0 + r] = at;
-            cursor[r] = at;
-            at += c[r];
-            end[r] = at;
-        }
+        for (int r = 0; r < KPT; r++) end[r] = (k0 + r < Z) ? w.seg_count[t0 + k0 + r] : 0u;
     }
 
     int lo = 0, hi = Z;
@@ -239,7 +233,8 @@ __device__ __forceinline__ void walk_stack_warp(const WalkParams &w, const long 
             z_after[r] = in_window ? z : zh[r];
             crossing |= (in_window && !same) ? (1u << r) : 0u;
             pcode[r] = 0;
-            if (FILL) pcode[r] = emit_geometry<FAST>(w, zh[r], s_full, cursor[r], in_window && same && cursor[r] < end[r]);
+            if (FILL)
+                pcode[r] = emit_geometry<FAST>(w, zh[r], s_full, base + cursor[r] * w.Zs + k, in_window && same && cursor[r] < end[r]);
         }
         if (last) {
 #pragma unroll
@@ -256,7 +251,7 @@ __device__ __forceinline__ void walk_stack_warp(const WalkParams &w, const long 
                 crossing &= crossing - 1;
                 const int k = k0 + r;
                 const float home = UP ? __fmul_rn(w.z_sep, (float)k) : __fmul_rn(w.z_sep, (float)(k + 1));
-                const uint32_t slot0 = pick<KPT>(cursor, r), slot_end = pick<KPT>(end, r);
+                const uint32_t j0 = pick<KPT>(cursor, r), j_end = pick<KPT>(end, r);
                 float s = s_full, z_cur = pick<KPT>(zh, r);
                 int c = interval_of<UP, FAST>(w, z_cur);
                 uint32_t made = 0, pc = 0;
@@ -282,8 +277,8 @@ __device__ __forceinline__ void walk_stack_warp(const WalkParams &w, const long 
                         }
                     }
                     if (FILL) {
-                        const uint32_t slot = slot0 + made;
-                        const bool store = slot < slot_end;
+                        const uint32_t slot = base + (j0 + made) * w.Zs + k;
+                        const bool store = j0 + made < j_end;
                         const uint32_t byte = emit_geometry<FAST>(w, z_cur, ds, slot, store);
                         if (made < 4) pc |= byte << (8 * made);
                         else if (store) w.rec_code[slot] = byte << 24;   // fifth and later: parked in the record
@@ -349,9 +344,9 @@ __device__ __forceinline__ void walk_stack_warp(const WalkParams &w, const long 
                     cnt_r = pick<KPT>(cnt, r);
                     pc = pick<KPT>(pcode, r);
                     ser = serial_at + pick<KPT>(first_serial, r);
-                    cur = pick<KPT>(cursor, r);
+                    cur = base + pick<KPT>(cursor, r) * w.Zs + (k0 + r);
                 }
-                const uint32_t slot = cur + m;
+                const uint32_t slot = cur + m * w.Zs;
                 const uint32_t byte = m < 4 ? ((pc >> (8 * m)) & 0xffu) : (w.rec_code[slot] >> 24);
                 const unsigned long long serial = ser + m;
                 const uint32_t draw = moc_rand31(w.seed, w.rand_base + serial);
@@ -412,7 +407,14 @@ __device__ __forceinline__ void walk_stack_warp(const WalkParams &w, const long 
         unsigned long long tot = mine;
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, d);
-        if (lane == 0) w.pair_count[pair] = tot;
+        uint32_t longest = 0;
+#pragma unroll
+        for (int r = 0; r < KPT; r++) longest = max(longest, made_total[r]);
+        longest = __reduce_max_sync(0xffffffffu, longest);
+        if (lane == 0) {
+            w.pair_count[pair] = tot;
+            w.pair_max[pair] = longest;   // the longest ray decides how many record rows the stack needs
+        }
     }
 }
 
