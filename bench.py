@@ -391,6 +391,15 @@ def run_moc(args):
     integrations = segs * G
     value = integrations / (ms * 1e-3)
 
+    leakage = dev.leakage
+    # ---- the measured ceiling of K1's memory side (needs the resident handle: before the e2e leg)
+    l2_probe = None
+    try:
+        if inp.fai >= 3 and inp.axial_exp == 2:
+            l2_probe = (dev.probe_l2_gather(0), dev.probe_l2_gather(1))
+    except Exception as e:   # diagnostics only
+        l2_probe = str(e)
+
     # ---- end to end through the reference's own entry point on host structures (rank-local)
     e2e = None
     if not args.no_e2e:
@@ -418,17 +427,15 @@ def run_moc(args):
             "note": "not HBM-bound: FP32 issue + L2 gather/atomic bound (DESIGN.md 'roofline')"}
     # the measured ceiling of the kernel's memory side: the same gathers + vector reductions on the
     # same (L2-resident) slab without the arithmetic, timed live (moc_probe_l2_gather)
-    try:
-        if inp.fai >= 3 and inp.axial_exp == 2:
-            probe_mix, probe_rd = dev.probe_l2_gather(1), dev.probe_l2_gather(0)
-            G4 = (G // 32) * 32 if G >= 32 else G     # the probe moves whole 128-byte quads
-            iface = my_integ * 20.0 / att_s / 1e9 if att_s else None   # 16 B gathered + 4 B reduced per integration
-            roof["l2"].update({"sm_l2_interface_bytes_per_integration": 20, "achieved_interface_gbs": iface,
-                               "probe_gather_gbs": probe_rd / 1e9, "probe_gather_plus_red_gbs": probe_mix / 1e9,
-                               "frac_of_probe": iface / (probe_mix / 1e9) if iface else None,
-                               "probe": "moc_probe_l2_gather: K1's access pattern on the same slab, no arithmetic"})
-    except Exception as e:   # diagnostics only
-        roof["l2"]["probe_error"] = str(e)
+    if isinstance(l2_probe, tuple):
+        probe_rd, probe_mix = l2_probe
+        iface = my_integ * 20.0 / att_s / 1e9 if att_s else None   # 16 B gathered + 4 B reduced per integration
+        roof["l2"].update({"sm_l2_interface_bytes_per_integration": 20, "achieved_interface_gbs": iface,
+                           "probe_gather_gbs": probe_rd / 1e9, "probe_gather_plus_red_gbs": probe_mix / 1e9,
+                           "frac_of_probe": iface / (probe_mix / 1e9) if iface else None,
+                           "probe": "moc_probe_l2_gather: K1's access pattern on the same slab, no arithmetic"})
+    elif l2_probe is not None:
+        roof["l2"]["probe_error"] = l2_probe
     roof["frac"] = roof["achieved"] / hbm_peak if roof["achieved"] else None
 
     cpu = None
@@ -449,10 +456,11 @@ def run_moc(args):
                                    " + renormalize_flux + update_sources + compute_keff",
                            "ntracks_per_gpu": T3, "n_egroups": G,
                            "segments_per_sweep_per_gpu": state["segments"] // n_launch,
-                           "l2": "inputs larger than L2 (12.9 GB angular flux + 23 GB segment records "
-                                 "streamed per step); no flush",
+                           "l2": f"inputs larger than L2 ({8e-9 * T3 * G:.1f} GB angular flux + "
+                                 f"{12e-9 * state['segments'] / n_launch:.1f} GB segment records streamed per "
+                                 "step, 126 MB L2); no flush",
                            "host_build_s": round(build_s, 1)},
-                "ns_per_integration": 1e9 / value, "keff": state["keff"], "leakage": dev.leakage,
+                "ns_per_integration": 1e9 / value, "keff": state["keff"], "leakage": leakage,
                 "sweep_ms": state["sweep_ms"] / n_launch,
                 "phases_ms": {"count": state["count_ms"] / n_launch, "fill": state["fill_ms"] / n_launch,
                               "attenuate": state["att_ms"] / n_launch},

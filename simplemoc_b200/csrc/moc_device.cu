@@ -1077,7 +1077,13 @@ static int sweep_core(moc_handle *h, long *segments_processed, const HostLayout 
         if (overlap_grid && !io && b.last_of_chunk && b.end == std::max<long long>(boundary_pairs, 1) &&
             (boundary_pairs < pairs || bi + 1 == batches.size()) && !e_exchanged) {
             // every track the exchange touches has its outgoing flux: exchange under the interior sweep
-            if (!h->comm_stream) CUDA_TRY(cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking));
+            if (!h->comm_stream) {
+                // highest priority: the exchange's small kernels and NCCL's copy kernels take SM slots as
+                // they free up instead of queueing behind the interior sweep's ~5e5 pending CTAs
+                int least = 0, greatest = 0;
+                CUDA_TRY(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+                CUDA_TRY(cudaStreamCreateWithPriority(&h->comm_stream, cudaStreamNonBlocking, greatest));
+            }
             CUDA_TRY(cudaStreamWaitEvent(h->comm_stream, ev_b[3 * bi + 2], 0));
             if ((rc = exchange_on_stream(h, overlap_grid, h->comm_stream))) return rc;
             if ((rc = event_at(h, ev_next++, &e_exchanged))) return rc;
