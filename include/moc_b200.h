@@ -172,6 +172,11 @@ void moc_dropin_configure(unsigned long long seed, unsigned long long rand_base,
 int moc_set_device(int device);
 /* 1: keep results on the device between the calls above; 0 (default): write back */
 void moc_set_resident(int on);
+/* Resident mode only: tell the library the neighbour table before the loop.  transport_sweep then
+ * starts the boundary exchange (comms.c:5-196) as soon as the z-stacks it moves are swept and runs it
+ * under the sweep of the interior stacks; the fast_transfer_boundary_fluxes call that follows with the
+ * same grid only collects it.  NULL switches the overlap off. */
+void moc_dropin_set_grid(const CommGrid *grid);
 /* download everything the phases run so far have mutated into the host Params */
 int moc_sync_to_host(Params *params);
 /* forget (and free) the device mirror that belongs to this Params */

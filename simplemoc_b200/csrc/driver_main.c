@@ -150,6 +150,8 @@ int main(int argc, char *argv[])
                 fclose(f);
             }
             if (moc_comm_init(moc_handle_of(&params), nranks, rank, id)) die("nccl init");
+            /* from the next iteration on the exchange runs under the sweep of the interior stacks */
+            if (!host_buffers) moc_dropin_set_grid(&grid);
         }
         if (nranks > 1) {
             a = now();

@@ -1674,12 +1674,23 @@ struct Mirror {
     bool dirty_sweep = false;   // device holds newer psi/z/flux than the host
     bool dirty_all = false;     // device holds newer everything
     std::vector<void *> registered;   // host slabs this library page-locked (cudaHostRegister)
+    bool exchanged = false;           // the last transport_sweep already ran the boundary exchange
 };
 static std::mutex g_mirror_mutex;
 static std::unordered_map<const void *, Mirror> g_mirrors;   // keyed by Params.tracks
 static int g_resident = 0;
 static unsigned long long g_dropin_seed = 1, g_dropin_rand_base = 0;
 static int g_dropin_exp_mode = 0, g_dropin_source_stride = 48;
+static CommGrid g_dropin_grid;
+static bool g_dropin_grid_set = false;
+
+// With the grid known in advance (resident mode), transport_sweep starts the boundary exchange under
+// the sweep of the interior stacks and the following fast_transfer_boundary_fluxes only collects it.
+extern "C" void moc_dropin_set_grid(const CommGrid *grid)
+{
+    g_dropin_grid_set = grid != nullptr;
+    if (grid) g_dropin_grid = *grid;
+}
 
 extern "C" void moc_set_resident(int on) { g_resident = on ? 1 : 0; }
 
@@ -1772,7 +1783,15 @@ extern "C" void transport_sweep(Params *params, Input *I)
     long segs = 0;
     // non-resident: uploads, kernels and downloads are pipelined inside the sweep; the call
     // returns after the last byte is back in the host structures
-    if (sweep_core(m.h, &segs, g_resident ? nullptr : &L)) die("transport_sweep");
+    const CommGrid *ahead = nullptr;
+    if (g_resident && g_dropin_grid_set) {
+        const int *nb = &g_dropin_grid.x_pos_src;
+        bool peers = false;
+        for (int q = 0; q < 12; q++) peers = peers || nb[q] >= 0;
+        if (!peers || m.h->nccl_comm) ahead = &g_dropin_grid;   // neighbours need moc_comm_init first
+    }
+    if (sweep_core(m.h, &segs, g_resident ? nullptr : &L, ahead)) die("transport_sweep");
+    m.exchanged = ahead != nullptr;
     I->segments_processed = segs;
     if (g_resident) m.dirty_sweep = true;
 }
@@ -1819,6 +1838,11 @@ extern "C" void fast_transfer_boundary_fluxes(Params params, Input I, CommGrid g
 {
     HostLayout L;
     Mirror &m = mirror_for(&params, &I, L, true, "fast_transfer_boundary_fluxes");
+    if (g_resident && m.exchanged && g_dropin_grid_set && memcmp(&grid, &g_dropin_grid, sizeof(CommGrid)) == 0) {
+        m.exchanged = false;   // done under the sweep (moc_dropin_set_grid)
+        m.dirty_all = true;
+        return;
+    }
     if (moc_exchange(m.h, &grid)) die("fast_transfer_boundary_fluxes");
     if (g_resident) m.dirty_all = true;
     else if (download_into(m.h, L, &params, 2)) die("fast_transfer_boundary_fluxes");

@@ -63,6 +63,36 @@ def test_overlapped_sweep_exchange_equals_two_calls(built):
     a.close(); b.close(); host.close()
 
 
+def test_dropin_loop_overlaps_the_exchange_when_told_the_grid(built):
+    """The reference's loop (main.c:57-92) under the drop-in names, resident: with
+    moc_dropin_set_grid the exchange runs inside transport_sweep and the following
+    fast_transfer_boundary_fluxes only collects it -- same slab and leakage as the handle API."""
+    L = api.lib()
+    vals = CASES["exch"]
+    host = m.HostProblem(m.derive(m.input_from_values(vals)), seed=8)
+    ref = m.DeviceProblem(host, device=0)
+    grid = m.make_grid(1, 1, 1, 0)
+    n_ref = ref.sweep()
+    ref.exchange(grid)
+    L.moc_dropin_configure(host.seed, host.rand_calls, 0, 48)
+    L.moc_set_resident(1)
+    L.moc_dropin_set_grid(C.byref(grid))
+    inp = type(host.I).from_buffer_copy(host.I)
+    L.transport_sweep(C.byref(host.P), C.byref(inp))
+    mirror = L.moc_handle_of(C.byref(host.P))
+    before = L.moc_get_launch_count(mirror)
+    L.fast_transfer_boundary_fluxes(host.P, inp, grid)              # nothing left to do
+    assert L.moc_get_launch_count(mirror) == before
+    assert inp.segments_processed == n_ref
+    assert L.moc_sync_to_host(C.byref(host.P)) == 0
+    assert np.array_equal(host.get(api.ARR_PSI).ravel(), ref.get(api.ARR_PSI).ravel())
+    assert host.P.leakage[0] == ref.leakage and ref.leakage != 0
+    L.moc_dropin_set_grid(None)
+    L.moc_set_resident(0)
+    assert L.moc_release(C.byref(host.P)) == 0
+    ref.close(); host.close()
+
+
 def test_exchange_needs_a_communicator(built):
     host = m.HostProblem(m.derive(m.input_from_values(CASES["exch"])), seed=6)
     dev = m.DeviceProblem(host, device=0)
