@@ -77,6 +77,9 @@ def parse_args():
                     help="override n_egroups (BASELINE config 4: 32 / 64 / 128 on the default geometry)")
     ap.add_argument("--decomp-ax", type=int, default=0,
                     help="override decomp_assemblies_ax (BASELINE config 5: 2 = ~131 GB per GPU)")
+    ap.add_argument("--device-build", action="store_true",
+                    help="generate the problem on the device (moc_create_synthetic); implies --no-e2e: there "
+                         "are no host structures to run the drop-in call on")
     ap.add_argument("--grid", default="", help="cx,cy,cz (default: 1x1x1, 2x1x1, 2x2x1, 2x2x2)")
     return ap.parse_args()
 
@@ -326,9 +329,14 @@ def run_moc(args):
     inp.mype = rank
     inp = m.derive(inp, args.limit_tracks_2d)
     t0 = time.time()
-    host = m.HostProblem(inp, seed=1 + rank)          # every rank: a full-size domain of its own
-    dev = m.DeviceProblem(host, device=local,
-                          exp_mode=api.EXP_SFU if args.exp == "sfu" else api.EXP_TABLE_REF)
+    exp_mode = api.EXP_SFU if args.exp == "sfu" else api.EXP_TABLE_REF
+    if args.device_build:
+        args.no_e2e = True
+        host = None
+        dev = m.DeviceProblem.synthetic(inp, seed=1 + rank, device=local, exp_mode=exp_mode)
+    else:
+        host = m.HostProblem(inp, seed=1 + rank)          # every rank: a full-size domain of its own
+        dev = m.DeviceProblem(host, device=local, exp_mode=exp_mode)
     build_s = time.time() - t0
     cx, cy, cz = grid_for(world, args.grid)
     grid = m.make_grid(cx, cy, cz, rank)
@@ -459,7 +467,7 @@ def run_moc(args):
                            "l2": f"inputs larger than L2 ({8e-9 * T3 * G:.1f} GB angular flux + "
                                  f"{12e-9 * state['segments'] / n_launch:.1f} GB segment records streamed per "
                                  "step, 126 MB L2); no flush",
-                           "host_build_s": round(build_s, 1)},
+                           "build_s": round(build_s, 1), "built_on": "device" if args.device_build else "host"},
                 "ns_per_integration": 1e9 / value, "keff": state["keff"], "leakage": leakage,
                 "sweep_ms": state["sweep_ms"] / n_launch,
                 "phases_ms": {"count": state["count_ms"] / n_launch, "fill": state["fill_ms"] / n_launch,
@@ -470,7 +478,8 @@ def run_moc(args):
             line["config"]["limit_tracks_2d"] = args.limit_tracks_2d
         print(json.dumps(finite(line), allow_nan=False), flush=True)
     dev.close()
-    host.close()
+    if host is not None:
+        host.close()
     if dist is not None:
         dist.destroy_process_group()
 

@@ -237,6 +237,13 @@ typedef struct {
 
 /* Upload the problem described by the reference-layout host structures. */
 int moc_create(const Input *I, const Params *P, int device, moc_handle **out);
+/* The same synthetic problem as moc_build_tracks + moc_create, generated on the device (the
+ * reference's build_tracks(), init.c:106-159, with every rand() draw taken from its position in the
+ * counter stream): no host copy of the 3D-track and source arrays ever exists.  Only the handle API
+ * works on such a handle (there are no host structures to write back to).  *rand_calls receives the
+ * stream position after construction (the handle already uses it). */
+int moc_create_synthetic(const Input *I, unsigned long long seed, int device, moc_handle **out,
+                         unsigned long long *rand_calls);
 int moc_destroy(moc_handle *h);
 int moc_set_option(moc_handle *h, int option, long value);
 long moc_get_option(moc_handle *h, int option);

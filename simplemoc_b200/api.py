@@ -91,7 +91,7 @@ EXPORTED = [
     "transport_sweep", "renormalize_flux", "update_sources", "compute_keff",
     "fast_transfer_boundary_fluxes", "moc_dropin_configure", "moc_set_device", "moc_handle_of",
     "moc_set_resident", "moc_dropin_set_grid", "moc_sync_to_host", "moc_release",
-    "moc_create", "moc_destroy", "moc_set_option", "moc_get_option", "moc_sweep",
+    "moc_create", "moc_create_synthetic", "moc_destroy", "moc_set_option", "moc_get_option", "moc_sweep",
     "moc_renormalize", "moc_update_sources", "moc_compute_keff", "moc_exchange", "moc_sweep_exchange",
     "moc_get_sweep_timing", "moc_get_array", "moc_set_array", "moc_download", "moc_upload",
     "moc_get_leakage", "moc_synchronize", "moc_get_stream", "moc_get_launch_count", "moc_probe_l2_gather", "moc_comm_get_unique_id", "moc_comm_init",
@@ -132,6 +132,7 @@ def lib():
     L.moc_params_set.restype = C.c_long
     L.moc_params_set.argtypes = [ip, C.POINTER(Params), C.c_int, vp, C.c_size_t]
     L.moc_create.argtypes = [ip, C.POINTER(Params), C.c_int, C.POINTER(vp)]
+    L.moc_create_synthetic.argtypes = [ip, C.c_uint64, C.c_int, C.POINTER(vp), C.POINTER(C.c_uint64)]
     L.moc_destroy.argtypes = [vp]
     L.moc_set_option.argtypes = [vp, C.c_int, C.c_long]
     L.moc_get_option.restype = C.c_long
@@ -294,6 +295,20 @@ class DeviceProblem:
         self.set_option(OPT_SEED, host.seed)
         self.set_option(OPT_RAND_BASE, host.rand_calls)
         self.set_option(OPT_EXP_MODE, exp_mode)
+
+    @classmethod
+    def synthetic(cls, inp, seed=1, device=0, exp_mode=EXP_TABLE_REF):
+        """the problem of HostProblem(inp, seed) generated on the device (moc_create_synthetic)"""
+        self = cls.__new__(cls)
+        self.host = None
+        self.I = inp
+        self.h = C.c_void_p()
+        calls = C.c_uint64(0)
+        _check(lib().moc_create_synthetic(C.byref(inp), seed, device, C.byref(self.h), C.byref(calls)),
+               "moc_create_synthetic")
+        self.seed, self.rand_calls = seed, calls.value
+        self.set_option(OPT_EXP_MODE, exp_mode)
+        return self
 
     def close(self):
         if self.h:

@@ -290,7 +290,7 @@ static int inspect_layout(const Input *I, const Params *P, int source_stride, Ho
 
 // ------------------------------------------------------------------ create / destroy
 
-static int upload_static(moc_handle *h, const Params *P, const HostLayout &L)
+static int upload_static(moc_handle *h, const Params *P, const HostLayout &L, bool synthetic = false)
 {
     const long long T2 = h->T2;
     const int Pn = h->P, G = h->G;
@@ -349,10 +349,12 @@ static int upload_static(moc_handle *h, const Params *P, const HostLayout &L)
     if ((rc = dev_alloc(&h->d.scatter, (size_t)h->X * G * G))) return rc;
     if ((rc = dev_alloc(&h->d.xs_index, (size_t)h->N))) return rc;
     if ((rc = dev_alloc(&h->d.vol, (size_t)h->N))) return rc;
-    CUDA_TRY(cudaMemcpy(h->d.xs, L.xs, sizeof(float) * (size_t)h->X * G * 3, cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMemcpy(h->d.scatter, L.scatter, sizeof(float) * (size_t)h->X * G * G, cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMemcpy(h->d.xs_index, L.xs_index.data(), sizeof(int) * (size_t)h->N, cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMemcpy(h->d.vol, L.vol.data(), sizeof(float) * (size_t)h->N, cudaMemcpyHostToDevice));
+    if (!synthetic) {
+        CUDA_TRY(cudaMemcpy(h->d.xs, L.xs, sizeof(float) * (size_t)h->X * G * 3, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(h->d.scatter, L.scatter, sizeof(float) * (size_t)h->X * G * G, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(h->d.xs_index, L.xs_index.data(), sizeof(int) * (size_t)h->N, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(h->d.vol, L.vol.data(), sizeof(float) * (size_t)h->N, cudaMemcpyHostToDevice));
+    }
 
     // exponential table (utils.c:48-78), as built by the caller
     h->table_dx = P->expTable.dx;
@@ -440,9 +442,17 @@ static int verify_fast_intervals(moc_handle *h)
     return MOC_OK;
 }
 
+static int need_track_image(moc_handle *h)
+{
+    if (h->d.track_image) return MOC_OK;
+    return dev_alloc(&h->d.track_image, (size_t)h->T3);
+}
+
 static int upload_mutable(moc_handle *h, const HostLayout &L, bool with_backward_psi)
 {
     const size_t T3 = (size_t)h->T3, G = (size_t)h->G;
+    int rc_img = need_track_image(h);
+    if (rc_img) return rc_img;
     // Track AoS image -> SoA on the device
     CUDA_TRY(cudaMemcpyAsync(h->d.track_image, L.tracks, sizeof(TrackImage) * T3, cudaMemcpyHostToDevice, h->stream));
     const int threads = 256;
@@ -482,8 +492,10 @@ extern "C" int moc_destroy(moc_handle *h)
     return MOC_OK;
 }
 
+// synthetic: Params holds only the 2D tracks, the polar angles and the table (moc_build_tracks_2d);
+// the 3D-track and source arrays are generated on the device by the caller (moc_create_synthetic)
 static int create_common(const Input *I, const Params *P, int device, int source_stride, moc_handle **out,
-                         HostLayout &L)
+                         HostLayout &L, bool synthetic = false)
 {
     int rc = require_device(device);
     if (rc) return rc;
@@ -505,7 +517,7 @@ static int create_common(const Input *I, const Params *P, int device, int source
         moc_set_error("source slab has more than 2^32 elements (the attenuation kernel indexes it with 32 bits)");
         return MOC_EINVAL;
     }
-    if ((rc = inspect_layout(I, P, source_stride, L))) return rc;
+    if (!synthetic && (rc = inspect_layout(I, P, source_stride, L))) return rc;
     CUDA_TRY(cudaSetDevice(device));
     moc_handle *h = new moc_handle();
     h->device = device;
@@ -534,11 +546,12 @@ static int create_common(const Input *I, const Params *P, int device, int source
             moc_set_error("cudaEventCreate failed");
             return fail(MOC_ECUDA);
         }
-    if ((rc = upload_static(h, P, L))) return fail(rc);
+    if ((rc = upload_static(h, P, L, synthetic))) return fail(rc);
     if ((rc = verify_fast_intervals(h))) return fail(rc);
     const size_t T3 = (size_t)h->T3, G = (size_t)h->G, N = (size_t)h->N, F = (size_t)h->F;
     const size_t pairs = (size_t)h->T2 * h->P;
-    if ((rc = dev_alloc(&h->d.track_image, T3))) return fail(rc);
+    // the 40-byte Track image only exists for problems that live in host structures
+    if (!synthetic && (rc = dev_alloc(&h->d.track_image, T3))) return fail(rc);
     if ((rc = dev_alloc(&h->d.p_weight, T3))) return fail(rc);
     if ((rc = dev_alloc(&h->d.z_height, T3))) return fail(rc);
     if ((rc = dev_alloc(&h->d.psi, 2 * T3 * G))) return fail(rc);
@@ -584,6 +597,49 @@ extern "C" int moc_create(const Input *I, const Params *P, int device, moc_handl
         return rc;
     }
     CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return MOC_OK;
+}
+
+// the synthetic problem of build_tracks() (init.c:106-159) generated where it is
+// used.  The reference fills 13-129 GB of arrays with rand() on one host thread; with the counter
+// RNG (include/moc_rng.h) every element knows its own draw number, so the
+// device fills them in parallel -- bit-identical to moc_build_tracks + moc_create
+// (tests/test_gpu_parity.py::test_device_construction_is_bit_identical).  The 2D tracks, the polar
+// angles and the exponential table stay on the host: they are small and depend on the host libm.
+extern "C" int moc_create_synthetic(const Input *I, unsigned long long seed, int device, moc_handle **out,
+                                    unsigned long long *rand_calls)
+{
+    if (!I || !out) {
+        moc_set_error("moc_create_synthetic: null argument");
+        return MOC_EINVAL;
+    }
+    Params lite;
+    moc_draw_layout at;
+    int rc = moc_build_tracks_2d(I, seed, &lite, &at);
+    if (rc) return rc;
+    HostLayout L;
+    rc = create_common(I, &lite, device, 48, out, L, true);
+    Params tmp = lite;
+    moc_free_tracks(I, &tmp);   // the handle has copied what it needs
+    if (rc) return rc;
+    moc_handle *h = *out;
+    const long long T3 = h->T3, N = h->N, X = h->X;
+    const int G = h->G, F = h->F, threads = 256;
+    auto blocks = [&](long long n) { return (unsigned)std::min<long long>((n + threads - 1) / threads, 148ll * 64); };
+    synth_tracks_kernel<<<blocks(T3), threads, 0, h->stream>>>(h->d.p_weight, h->d.z_height, T3, h->Z, h->P,
+                                                              h->I.axial_z_sep, seed, at.p_weight);
+    CUDA_TRY(cudaMemsetAsync(h->d.psi, 0, sizeof(float) * 2 * (size_t)T3 * G, h->stream));   // tracks.c:106-115
+    synth_rows_kernel<<<blocks(N * F * G), threads, 0, h->stream>>>(h->d.src, N * F, G, h->Gp, seed, at.fine_source);
+    synth_rows_kernel<<<blocks(N * G), threads, 0, h->stream>>>(h->d.src + (size_t)2 * N * F * h->Gp, N, G, h->Gp, seed, at.sigT);
+    synth_rows_kernel<<<blocks(X * G * G), threads, 0, h->stream>>>(h->d.scatter, X * G * G, 1, 1, seed, at.scatter);
+    synth_rows_kernel<<<blocks(X * G * 3), threads, 0, h->stream>>>(h->d.xs, X * G * 3, 1, 1, seed, at.xs);
+    synth_regions_kernel<<<blocks(N), threads, 0, h->stream>>>(h->d.xs_index, h->d.vol, N, X, seed, at.regions);
+    h->launch_count += 7;
+    h->seed = seed;
+    h->rand_base = at.end;
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    CUDA_TRY(cudaGetLastError());
+    if (rand_calls) *rand_calls = at.end;
     return MOC_OK;
 }
 
@@ -1388,6 +1444,10 @@ static int download_into(moc_handle *h, const HostLayout &L, Params *P, int what
 {
     const size_t T3 = (size_t)h->T3, G = (size_t)h->G, N = (size_t)h->N, F = (size_t)h->F;
     const int threads = 256;
+    if (!h->d.track_image) {
+        moc_set_error("this handle was generated on the device (moc_create_synthetic): there are no host Track structures to write back to");
+        return MOC_EINVAL;
+    }
     patch_tracks_kernel<<<(unsigned)((T3 + threads - 1) / threads), threads, 0, h->stream>>>(
         h->d.track_image, (long long)T3, h->d.z_height);
     CUDA_TRY(cudaMemcpyAsync((void *)L.tracks, h->d.track_image, sizeof(TrackImage) * T3, cudaMemcpyDeviceToHost, h->stream));

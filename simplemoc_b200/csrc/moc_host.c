@@ -296,6 +296,66 @@ static int make_exp_table(Table *tab, float precision, float maxVal)
     return MOC_OK;
 }
 
+/* The cheap, libm-dependent part of build_tracks(): 2D tracks (tracks.c:4-58), polar angles
+ * (tracks.c:159-168), the exponential table (utils.c:48-78), the leakage cell -- plus the stream
+ * positions of every later block of draws.  Params.tracks and Params.sources stay NULL: the
+ * device fills those arrays itself (moc_create_synthetic). */
+int moc_build_tracks_2d(const Input *in, uint64_t seed, Params *out, moc_draw_layout *layout)
+{
+    if (in->load_tracks || in->ntracks_2D <= 0 || in->z_stacked <= 0 || in->n_polar_angles <= 0 ||
+        in->n_egroups <= 0 || in->fai <= 0 || in->n_source_regions_per_node < 8) {
+        moc_set_error("degenerate problem: T2=%ld Z=%d P=%d G=%d fai=%d N=%ld (need N >= 8, no track file)",
+                      in->ntracks_2D, in->z_stacked, in->n_polar_angles, in->n_egroups,
+                      in->fai, in->n_source_regions_per_node);
+        return MOC_EINVAL;
+    }
+    const long T2 = in->ntracks_2D, T3 = in->ntracks, N = in->n_source_regions_per_node;
+    const long X = N / 8;
+    const int P = in->n_polar_angles, G = in->n_egroups, F = in->fai;
+    memset(out, 0, sizeof *out);
+    moc_draw_layout at;
+    at.az_weight = 0;
+    at.n_segments = at.az_weight + (uint64_t)T2;
+    at.seg_length = at.n_segments + 2 * (uint64_t)T2;
+    Track2D *t2 = (Track2D *)calloc((size_t)T2, sizeof(Track2D));
+    if (!t2) return MOC_ENOMEM;
+    long total_segments = 0;
+    for (long i = 0; i < T2; i++) {
+        t2[i].az_weight = moc_urand(seed, at.az_weight + (uint64_t)i);
+        t2[i].n_segments = normal_draw(seed, at.n_segments + 2 * (uint64_t)i,
+                                       in->segments_per_track, sqrt(in->segments_per_track));
+        if (t2[i].n_segments < 0) t2[i].n_segments = 0;
+        total_segments += t2[i].n_segments;
+    }
+    Segment *segs = (Segment *)calloc((size_t)(total_segments > 0 ? total_segments : 1), sizeof(Segment));
+    if (!segs) return MOC_ENOMEM;
+    long first = 0;
+    for (long i = 0; i < T2; i++) {
+        t2[i].segments = segs + first;
+        for (long n = 0; n < t2[i].n_segments; n++)
+            segs[first + n].length = moc_urand(seed, at.seg_length + (uint64_t)(first + n))
+                                     * in->assembly_width / t2[i].n_segments;
+        first += t2[i].n_segments;
+    }
+    out->tracks_2D = t2;
+    at.p_weight = at.seg_length + (uint64_t)total_segments;
+    float *polar = (float *)malloc(sizeof(float) * (size_t)P);
+    if (!polar) return MOC_ENOMEM;
+    for (int j = 0; j < P; j++) polar[j] = M_PI * (j + 0.5) / P;
+    out->polar_angles = polar;
+    at.scatter = at.p_weight + (uint64_t)T3;
+    at.xs = at.scatter + (uint64_t)X * G * G;
+    at.fine_source = at.xs + (uint64_t)X * G * 3;
+    at.sigT = at.fine_source + (uint64_t)N * F * G;
+    at.regions = at.sigT + (uint64_t)N * G;
+    at.end = at.regions + 2 * (uint64_t)N - 1;
+    out->leakage = (float *)calloc(1, sizeof(float));
+    int rc = make_exp_table(&out->expTable, in->precision, 10.0);
+    if (rc) return rc;
+    if (layout) *layout = at;
+    return MOC_OK;
+}
+
 /* init.c:106-159 = tracks.c:4-58 + tracks.c:75-168 + source.c:4-214 + utils.c:48-78 */
 int moc_build_tracks(const Input *in, uint64_t seed, Params *out, uint64_t *rand_calls)
 {

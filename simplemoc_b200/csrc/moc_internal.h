@@ -6,6 +6,8 @@
 #include <stddef.h>
 #include <stdint.h>
 
+#include "moc_b200.h"
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -33,6 +35,9 @@ typedef struct {
     uint64_t regions;      /* 2N-1 draws (index, volume)       source.c:183-198 */
     uint64_t end;          /* first draw of the sweep                            */
 } moc_draw_layout;
+
+/* 2D tracks, polar angles, exponential table and the draw layout only (moc_host.c) */
+int moc_build_tracks_2d(const Input *in, uint64_t seed, Params *out, moc_draw_layout *layout);
 
 #ifdef __cplusplus
 }

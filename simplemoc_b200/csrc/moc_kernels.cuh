@@ -642,6 +642,47 @@ __global__ void patch_tracks_kernel(TrackImage *img, long long n, const float *z
     img[t].z_height = z_height[t];
 }
 
+// ------------------------------------------------------------------ synthetic problem
+
+// tracks.c:117-148: p_weight = urand() in (i, j, k) order; upward rays start at the bottom of their
+// slot, downward rays at the top
+__global__ void synth_tracks_kernel(float *p_weight, float *z_height, long long T3, int Z, int P, float z_sep,
+                                    unsigned long long seed, unsigned long long first_draw)
+{
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < T3; t += stride) {
+        const int k = (int)(t % Z), j = (int)((t / Z) % P);
+        p_weight[t] = moc_urand(seed, first_draw + (unsigned long long)t);
+        z_height[t] = (j < P / 2) ? __fmul_rn(z_sep, (float)k) : __fmul_rn(z_sep, (float)(k + 1));
+    }
+}
+
+// dst[row * pitch + col] = urand(first_draw + row * cols + col): source.c:45-48, 83-86, 157-160, 170-172
+__global__ void synth_rows_kernel(float *dst, long long rows, int cols, int pitch, unsigned long long seed,
+                                  unsigned long long first_draw)
+{
+    const long long n = rows * cols, stride = (long long)gridDim.x * blockDim.x;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride) {
+        const long long row = e / cols;
+        dst[row * pitch + (e - row * cols)] = moc_urand(seed, first_draw + (unsigned long long)e);
+    }
+}
+
+// source.c:183-198: region 0 takes material 0 without a draw; region i > 0 draws (material, volume)
+__global__ void synth_regions_kernel(int *xs_index, float *vol, long long N, long long X, unsigned long long seed,
+                                     unsigned long long first_draw)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    if (i == 0) {
+        xs_index[0] = 0;
+        vol[0] = moc_urand(seed, first_draw);
+    } else {
+        xs_index[i] = (int)((long long)moc_rand31(seed, first_draw + 2ull * (unsigned long long)i - 1ull) % X);
+        vol[i] = moc_urand(seed, first_draw + 2ull * (unsigned long long)i);
+    }
+}
+
 // ------------------------------------------------------------------ K5: boundary exchange helpers
 
 // sums[b] = pairwise_sum(slab[offsets[b] .. +n))  -- one CTA of 256 threads per border chunk

@@ -151,6 +151,33 @@ def test_sfu_mode_against_exact_exp_oracle(built):
     dev.close(); host.close(); oracle.close()
 
 
+@pytest.mark.parametrize("case", ["tiny", "mini104", "tall"])
+def test_device_construction_is_bit_identical(built, case):
+    """moc_create_synthetic generates the 3D-track and source arrays on the device from the counter
+    RNG: every array, the sweep's integers and the reductions equal those of the
+    host construction (moc_build_tracks, reference init.c:106-159) uploaded with moc_create."""
+    inp = m.derive(m.input_from_values(CASES[case]))
+    host = m.HostProblem(inp, seed=17)
+    a = m.DeviceProblem(host, device=0)
+    b = m.DeviceProblem.synthetic(type(inp).from_buffer_copy(inp), seed=17, device=0)
+    assert b.rand_calls == host.rand_calls
+    for arr in (api.ARR_P_WEIGHT, api.ARR_Z_HEIGHT, api.ARR_FINE_SOURCE, api.ARR_SIGT, api.ARR_PSI, api.ARR_FINE_FLUX):
+        assert np.array_equal(a.get(arr), b.get(arr)), arr
+    a.set_option(api.OPT_DIGEST, 1); b.set_option(api.OPT_DIGEST, 1)
+    assert a.sweep() == b.sweep()
+    assert np.array_equal(a.get(api.ARR_SEG_COUNT), b.get(api.ARR_SEG_COUNT))
+    assert np.array_equal(a.get(api.ARR_QSR_DIGEST), b.get(api.ARR_QSR_DIGEST))
+    assert np.array_equal(a.get(api.ARR_PSI), b.get(api.ARR_PSI))
+    # materials (XS, scattering matrices, volumes, material indices) through the reductions, from
+    # identical tallies (the sweep's floating-point atomics are not ordered)
+    b.set(api.ARR_FINE_FLUX, a.get(api.ARR_FINE_FLUX))
+    a.renormalize(); b.renormalize()
+    assert a.update_sources(0.8) == b.update_sources(0.8)
+    assert np.array_equal(a.get(api.ARR_FINE_SOURCE), b.get(api.ARR_FINE_SOURCE))
+    assert a.compute_keff() == b.compute_keff()
+    a.close(); b.close(); host.close()
+
+
 def test_dropin_names_on_the_reference_own_structures(built):
     """The drop-in C-ABI (transport_sweep, renormalize_flux, update_sources, compute_keff under the
     reference's names) driven with the pointer-rich Params/Input that the UNMODIFIED reference's
