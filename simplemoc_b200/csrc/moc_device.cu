@@ -1818,6 +1818,8 @@ static Mirror &mirror_for(const Params *P, const Input *I, HostLayout &L, bool n
         int device = 0;
         cudaGetDevice(&device);
         if (create_common(I, P, device, g_dropin_source_stride, &m.h, L)) die(where);
+        if (const char *c = getenv("MOC_B200_STREAM_CHUNKS"))
+            if (atoi(c) >= 1 && atoi(c) <= 4096) m.h->stream_chunks = atoi(c);
         m.h->seed = g_dropin_seed;
         m.h->rand_base = g_dropin_rand_base;
         m.h->exp_mode = g_dropin_exp_mode;

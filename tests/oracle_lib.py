@@ -68,6 +68,16 @@ CASES = {
     # (more than a warp can own: the CTA-per-stack ray trace)
     "short": [3, 3, 4, 3, 2, 2.0, 16.0, 8, 4, 16, 0, 1, 10, 21.42, 400.0, 0.01, 200, 0],
     "tall": [3, 3, 4, 3, 2, 4.0, 2.0, 8, 4, 16, 0, 1, 10, 21.42, 400.0, 0.01, 200, 0],
+    # edge cases.  ragged: ~5 segments per 2D track, some tracks get NONE (seeds 2 and 4; a negative
+    # draw -- seeds 5, 6 -- is undefined behaviour in the reference itself, tracks.c:29-47, and is not a
+    # case).  polar1: a single polar angle, pi/2: every ray travels downward with cos ~ -4e-8.
+    # polar2: one upward and one downward angle.  onecell: one coarse axial interval (fai = 3 fine
+    # ones: every segment uses an edge stencil or the only interior row).  zone: one ray per stack.
+    "ragged": [3, 3, 4, 3, 2, 2.0, 4.0, 8, 4, 16, 0, 1, 5, 21.42, 400.0, 0.01, 200, 0],
+    "polar1": [3, 3, 4, 3, 2, 2.0, 4.0, 8, 1, 16, 0, 1, 10, 21.42, 400.0, 0.01, 200, 0],
+    "polar2": [3, 3, 2, 3, 2, 2.0, 8.0, 8, 2, 12, 0, 1, 10, 21.42, 400.0, 0.01, 200, 0],
+    "onecell": [3, 3, 1, 3, 2, 2.0, 4.0, 8, 4, 16, 0, 1, 10, 21.42, 400.0, 0.01, 200, 0],
+    "zone": [3, 3, 4, 3, 2, 2.0, 400.0, 8, 4, 16, 0, 1, 10, 21.42, 400.0, 0.01, 200, 0],
     # 96 000 short 3D tracks, G=8: large enough for one 10 000-track message per face
     # (comms.c:12-28), cheap to sweep -- the boundary-exchange case
     "exch": [3, 3, 4, 3, 2, 2.0, 0.05, 8, 4, 8, 1, 20, 10, 21.42, 400.0, 0.01, 200, 0],

@@ -129,6 +129,26 @@ def test_ray_trace_kernels_agree(built, case, walk, exact):
     dev.close(); host.close(); oracle.close()
 
 
+@pytest.mark.parametrize("case,seed,walk", [("ragged", 2, 0), ("ragged", 4, 1), ("polar1", 2, 0), ("polar1", 2, 1),
+                                            ("polar2", 2, 0), ("onecell", 2, 0), ("zone", 2, 0), ("zone", 2, 1)])
+def test_edge_cases(built, case, seed, walk):
+    """2D tracks without segments, a single (horizontal) polar angle, one coarse axial interval,
+    one ray per z-stack: integers exact, flux within tolerance, over two sweeps and the reductions."""
+    host, dev, oracle = make_pair(case, seed=seed, walk=walk)
+    for sweep in range(2):
+        assert dev.sweep() == oracle.sweep()
+        assert np.array_equal(dev.get(api.ARR_SEG_COUNT), oracle.seg_count)
+        assert np.array_equal(dev.get(api.ARR_QSR_DIGEST), oracle.digest)
+        assert np.array_equal(dev.get(api.ARR_Z_HEIGHT), oracle.z_height)
+        check_state(dev, oracle, f"{case} sweep {sweep}", frac_floor=0.99)
+        if sweep == 0:
+            dev.renormalize(); oracle.renormalize()
+            dev.update_sources(1.0); oracle.update_sources(1.0)
+            k_gpu, k_cpu = dev.compute_keff(), oracle.compute_keff()
+            assert abs(k_gpu - k_cpu) <= TOL * abs(k_cpu), (k_gpu, k_cpu)
+    dev.close(); host.close(); oracle.close()
+
+
 @pytest.mark.parametrize("lanes", [16, 32])
 def test_lane_mappings_agree(built, lanes):
     host, dev, oracle = make_pair("mini104", seed=9, lanes=lanes)
