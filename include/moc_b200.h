@@ -195,7 +195,8 @@ enum {
     MOC_ECUDA = -3,      /* CUDA runtime error (see moc_last_error)             */
     MOC_ENOMEM = -4,
     MOC_ELAYOUT = -5,    /* host Params is not laid out as the reference's slabs */
-    MOC_ECOMM = -6       /* NCCL error or communicator missing                  */
+    MOC_ECOMM = -6,      /* NCCL error or communicator missing                  */
+    MOC_EIO = -7         /* track file missing, truncated or corrupt            */
 };
 
 /* options for moc_set_option */
@@ -241,8 +242,9 @@ int moc_create(const Input *I, const Params *P, int device, moc_handle **out);
  * reference's build_tracks(), init.c:106-159, with every rand() draw taken from its position in the
  * counter stream): no host copy of the 3D-track and source arrays ever exists.  Only the handle API
  * works on such a handle (there are no host structures to write back to).  *rand_calls receives the
- * stream position after construction (the handle already uses it). */
-int moc_create_synthetic(const Input *I, unsigned long long seed, int device, moc_handle **out,
+ * stream position after construction (the handle already uses it).  With I->load_tracks the 2D tracks
+ * come from I->track_file and *I is updated like build_tracks(Input *) updates it (init.c:119-124). */
+int moc_create_synthetic(Input *I, unsigned long long seed, int device, moc_handle **out,
                          unsigned long long *rand_calls);
 int moc_destroy(moc_handle *h);
 int moc_set_option(moc_handle *h, int option, long value);
@@ -316,8 +318,17 @@ void moc_calculate_derived_inputs(Input *I);       /* src/init.c:4-30           
 size_t moc_est_mem_usage(const Input *I);          /* src/utils.c:97-143          */
 /* src/init.c:106-159 (+ tracks.c, source.c, utils.c:48-78): same slabs, same
  * draw order, draws taken from moc_rand31(seed, counter).  *rand_calls receives
- * the number of draws consumed (the serial-stream position at sweep start). */
-int moc_build_tracks(const Input *I, uint64_t seed, Params *out, uint64_t *rand_calls);
+ * the number of draws consumed (the serial-stream position at sweep start).
+ * Takes Input * like build_tracks(Input *): a track file (I->load_tracks) changes *I. */
+int moc_build_tracks(Input *I, uint64_t seed, Params *out, uint64_t *rand_calls);
+/* src/tracks.c:170-323 (the -d option): the 2D tracks of an OpenMOC track file.  Updates
+ * n_azimuthal, radial_ray_sep, ntracks_2D, segments_per_track and ntracks of *I as the reference
+ * does; az_weight of track u is draw az_weight_at + u of the counter stream (tracks.c:283).
+ * moc_build_tracks calls it when I->load_tracks is set (init.c:119-124).  A missing, truncated or
+ * implausible file returns MOC_EIO (the reference does not check).  Free with moc_free_tracks or
+ * free(tracks[0].segments); free(tracks). */
+int moc_load_openmoc_tracks(const char *fname, int cmfd, Input *I, uint64_t seed, uint64_t az_weight_at,
+                            Track2D **tracks, long *total_segments);
 void moc_free_tracks(const Input *I, Params *P);
 double moc_time_per_intersection(const Input *I, double seconds);   /* src/utils.c:147-155 */
 

@@ -57,8 +57,19 @@ static void quiet_end(int saved)
 /* Mirrors main(): set_default_input -> (-s) -> (-i file) -> derived -> build_tracks.
  * limit_tracks_2D > 0 shrinks the number of 2D tracks AFTER the derived inputs are
  * computed (bounded-sample timing; everything per-track is unchanged). */
+RefCase *ref_case_create_tracks(const char *input_file, int small, uint64_t seed,
+                                int nthreads, long limit_tracks_2D, const char *track_file);
+
 RefCase *ref_case_create(const char *input_file, int small, uint64_t seed,
                          int nthreads, long limit_tracks_2D)
+{
+    return ref_case_create_tracks(input_file, small, seed, nthreads, limit_tracks_2D, NULL);
+}
+
+/* track_file != NULL: what "-d <file>" does (src/io.c:160-168): the reference's own
+ * load_OpenMOC_tracks (src/tracks.c:170-323) supplies the 2D tracks. */
+RefCase *ref_case_create_tracks(const char *input_file, int small, uint64_t seed,
+                                int nthreads, long limit_tracks_2D, const char *track_file)
 {
     RefCase *c = (RefCase *)calloc(1, sizeof(RefCase));
     int saved = quiet_begin();
@@ -75,6 +86,10 @@ RefCase *ref_case_create(const char *input_file, int small, uint64_t seed,
     if (small) set_small_input(&c->I);
     if (input_file && input_file[0]) read_input_file(&c->I, (char *)input_file);
     c->I.nthreads = nthreads > 0 ? nthreads : 1;
+    if (track_file && track_file[0]) {
+        c->I.track_file = (char *)track_file;
+        c->I.load_tracks = true;
+    }
     calculate_derived_inputs(&c->I);
     if (limit_tracks_2D > 0 && limit_tracks_2D < c->I.ntracks_2D) {
         c->I.ntracks_2D = 2 * (limit_tracks_2D / 2);

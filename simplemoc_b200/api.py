@@ -97,7 +97,7 @@ EXPORTED = [
     "moc_get_leakage", "moc_synchronize", "moc_get_stream", "moc_get_launch_count", "moc_probe_l2_gather", "moc_comm_get_unique_id", "moc_comm_init",
     "moc_make_grid", "moc_exchange_plan", "moc_last_error", "moc_device_count", "moc_set_default_input",
     "moc_set_small_input", "moc_read_input_file", "moc_read_CLI",
-    "moc_calculate_derived_inputs", "moc_est_mem_usage", "moc_build_tracks",
+    "moc_calculate_derived_inputs", "moc_est_mem_usage", "moc_build_tracks", "moc_load_openmoc_tracks",
     "moc_free_tracks", "moc_time_per_intersection", "moc_params_get", "moc_params_set",
 ]
 
@@ -213,10 +213,14 @@ def small_input():
     return inp
 
 
-def input_from_values(values):
+def input_from_values(values, track_file=None):
+    """track_file: an OpenMOC track file, what `-d <file>` sets (src/io.c:160-168)"""
     inp = default_input()
     for name, v in zip(INPUT_FILE_FIELDS, values):
         setattr(inp, name, bool(v) if name == "decompose" else v)
+    if track_file:
+        inp.load_tracks = True
+        inp.track_file = os.fsencode(track_file)
     return inp
 
 

@@ -92,6 +92,17 @@ int main(int argc, char *argv[])
         rule();
         title("SimpleMOC-b200 : 3D MOC transport sweep on NVIDIA B200 (sm_100a)");
         rule();
+        if (input.load_tracks) printf("Reading track data from:\n%s\n", input.track_file);
+    }
+
+    Params params;
+    unsigned long long draws = 0;
+    double t0 = now();
+    if (moc_build_tracks(&input, seed + (unsigned long long)rank, &params, (uint64_t *)&draws)) die("build_tracks");
+    if (rank == 0) printf("Problem construction (host):          %6.2f sec\n", now() - t0);
+
+    if (rank == 0) {
+        /* after build_tracks, as main.c:32-36 does: a track file (-d) changes the track counts */
         title("INPUT SUMMARY");
         rule();
         printf("%-38s%d x %d x %d (this is rank %d)\n", "Spatial domains (GPUs):", cx, cy, cz, rank);
@@ -108,12 +119,6 @@ int main(int argc, char *argv[])
         printf("%-38s%llu\n", "Random stream seed:", seed);
         rule();
     }
-
-    Params params;
-    unsigned long long draws = 0;
-    double t0 = now();
-    if (moc_build_tracks(&input, seed + (unsigned long long)rank, &params, (uint64_t *)&draws)) die("build_tracks");
-    if (rank == 0) printf("Problem construction (host):          %6.2f sec\n", now() - t0);
 
     CommGrid grid;
     if (moc_make_grid(cx, cy, cz, rank, &grid)) die("grid");

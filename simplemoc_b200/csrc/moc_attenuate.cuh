@@ -8,9 +8,13 @@
  *     FMA-pipe/L2-bound (profiles/, DESIGN.md "K1");
  *   - every division is a multiplication by MUFU.RCP(sigT); the exponential is either the
  *     reference's table (shared memory, cell index bit-exact) or MUFU.EX2;
- *   - the gathered source rows (3 x G floats + sigT) are 128-byte-per-8-lanes float4 loads that
- *     hit in the 126 MB L2 (the whole source slab is L2-resident); tallies leave as 16-byte
- *     vector reductions (red.global.add.v4.f32).
+ *   - the quadratic fit of solver.c:74-76 depends on (source region, stencil, group) only, so it is
+ *     done once per sweep (fit_coefficients_kernel); per segment the kernel gathers the three
+ *     coefficient rows + sigT (4 x G floats) as 128-byte-per-8-lanes float4 loads that hit in the
+ *     126 MB L2 (coefficients 31 MB + sigT 3.5 MB + scalar flux 17 MB on the default problem);
+ *     tallies leave as 16-byte vector reductions (red.global.add.v4.f32);
+ *   - a lane's odd group (G = 104: 96 + lane) runs on scalar FP32 instructions, which take one
+ *     FMA-pipe cycle per warp instruction where a (half-empty) packed pair would take two.
  */
 #pragma once
 
@@ -35,6 +39,16 @@ __device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __
 __device__ __forceinline__ float2 mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
 __device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
 __device__ __forceinline__ float2 sub2(float2 a, float2 b) { return __fadd2_rn(a, neg2(b)); }
+// the same vocabulary on one float: the tail group of a lane (G = 104: 96 + lane) runs on scalar
+// FFMA/FMUL/FADD -- one FMA-pipe cycle per warp instruction instead of the two a packed pair takes
+__device__ __forceinline__ float neg2(float a) { return -a; }
+__device__ __forceinline__ float fma2(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+__device__ __forceinline__ float mul2(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float add2(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float sub2(float a, float b) { return __fadd_rn(a, -b); }
+template <typename V> __device__ __forceinline__ V splat(float v);
+template <> __device__ __forceinline__ float2 splat<float2>(float v) { return make_float2(v, v); }
+template <> __device__ __forceinline__ float splat<float>(float v) { return v; }
 
 // The table cell the reference picks for x (solver.c:1448): (int)(x / dx + 0.5f * dx), with an
 // IEEE float division.  EXACT_DIV: the division instruction sequence of __fdiv_rn.
@@ -77,9 +91,9 @@ struct TableConsts {
 // per-segment scalars of attenuate_fluxes, hoisted out of the group loop
 struct SegmentScalars {
     float ds;
-    float a1, a2;      // zin/(2dz), zin^2/(2dz^2)          : q0 = y2 + a1 (y1-y3) + a2 (y1-2y2+y3)
-    float b1, b2;      // mu/(2dz), 2 mu zin/(2dz^2)        : q1 mu
-    float b3;          // mu^2/(2dz^2)                       : q2 mu^2
+    float a1, a2;      // zin, zin^2                 : q0 = c0 + a1 c1 + a2 c2   (solver.c:79)
+    float b1, b2;      // mu, 2 mu zin               : q1 mu = b1 c1 + b2 c2     (solver.c:80)
+    float b3;          // mu^2                       : q2 mu^2 = b3 c2           (solver.c:81)
     float weight;
 };
 
@@ -88,80 +102,106 @@ struct SegmentScalars {
 //          is the reference's), IEEE division.
 //  MODE 1: the same with the verified fast division.
 //  MODE 2: SFU: MUFU.EX2.
-// All keep the reference's x > maxVal -> 1 rule (solver.c:1444-1445).  HI = false: only .x is live.
-template <int MODE, bool HI>
+// All keep the reference's x > maxVal -> 1 rule (solver.c:1444-1445).
+template <int MODE>
 __device__ __forceinline__ void one_minus_exp2(float2 x, const TableConsts &tc, float2 &E, float2 &D)
 {
     if (MODE == 2) {
         const float2 arg = mul2(x, bc(-1.4426950408889634f));
         D.x = x.x > tc.x_max ? 0.0f : ex2_approx(arg.x);
-        D.y = HI ? (x.y > tc.x_max ? 0.0f : ex2_approx(arg.y)) : 0.0f;
+        D.y = x.y > tc.x_max ? 0.0f : ex2_approx(arg.y);
         E = sub2(bc(1.0f), D);
     } else {
         float2 t;
         if (MODE == 0) {
             t.x = __fadd_rn(__fdiv_rn(x.x, tc.dx), tc.half_dx);
-            t.y = HI ? __fadd_rn(__fdiv_rn(x.y, tc.dx), tc.half_dx) : 0.0f;
+            t.y = __fadd_rn(__fdiv_rn(x.y, tc.dx), tc.half_dx);
         } else {
             float2 q = mul2(x, bc(tc.rdx));
             const float2 rem = fma2(neg2(q), bc(tc.dx), x);
             q = fma2(rem, bc(tc.rdx), q);
             t = add2(q, bc(tc.half_dx));
         }
-        int c0 = __float2int_rz(t.x);
+        int c0 = __float2int_rz(t.x), c1 = __float2int_rz(t.y);
         c0 = x.x > tc.x_max ? tc.n : c0;
-        float2 slope, icpt;
-        slope.x = tc.tab[2 * c0];          // two LDS.32 off one address: the halves of a packed
-        icpt.x = tc.tab[2 * c0 + 1];       // operand come from different cells, so no LDS.64
-        if (HI) {
-            int c1 = __float2int_rz(t.y);
-            c1 = x.y > tc.x_max ? tc.n : c1;
-            slope.y = tc.tab[2 * c1];
-            icpt.y = tc.tab[2 * c1 + 1];
-        } else {
-            slope.y = 0.0f;
-            icpt.y = 0.0f;
-        }
-        E = fma2(slope, x, icpt);
+        c1 = x.y > tc.x_max ? tc.n : c1;
+        // the halves of a packed operand come from different cells: one LDS.64 (slope, intercept) per group,
+        // and the interpolation on two scalar FFMA (the same two FMA-pipe cycles as one FFMA2, without the
+        // three register moves that re-pairing (slope0, slope1) / (intercept0, intercept1) costs)
+        const float2 e0 = *reinterpret_cast<const float2 *>(tc.tab + 2 * c0);
+        const float2 e1 = *reinterpret_cast<const float2 *>(tc.tab + 2 * c1);
+        E.x = __fmaf_rn(e0.x, x.x, e0.y);
+        E.y = __fmaf_rn(e1.x, x.y, e1.y);
         D = sub2(bc(1.0f), E);
     }
 }
 
-// Two energy groups of attenuate_fluxes (solver.c:66-82, 146-279) on packed FP32 pairs.
-// Returns the two tallies.  Same formulas as the reference, regrouped so that every factor that
-// does not depend on the group is a per-segment scalar and every division is a multiplication by
-// MUFU.RCP(sigT):
+// one group on scalar instructions (same modes, same cell selection)
+template <int MODE>
+__device__ __forceinline__ void one_minus_exp2(float x, const TableConsts &tc, float &E, float &D)
+{
+    if (MODE == 2) {
+        D = x > tc.x_max ? 0.0f : ex2_approx(__fmul_rn(x, -1.4426950408889634f));
+        E = __fadd_rn(1.0f, -D);
+    } else {
+        float t;
+        if (MODE == 0) {
+            t = __fadd_rn(__fdiv_rn(x, tc.dx), tc.half_dx);
+        } else {
+            float q = __fmul_rn(x, tc.rdx);
+            const float rem = __fmaf_rn(-q, tc.dx, x);
+            q = __fmaf_rn(rem, tc.rdx, q);
+            t = __fadd_rn(q, tc.half_dx);
+        }
+        int c = __float2int_rz(t);
+        c = x > tc.x_max ? tc.n : c;
+        const float2 e = *reinterpret_cast<const float2 *>(tc.tab + 2 * c);
+        E = __fmaf_rn(e.x, x, e.y);
+        D = __fadd_rn(1.0f, -E);
+    }
+}
+
+__device__ __forceinline__ float2 rcp_groups(float2 s) { return make_float2(rcp_approx(s.x), rcp_approx(s.y)); }
+__device__ __forceinline__ float rcp_groups(float s) { return rcp_approx(s); }
+
+// Energy groups of attenuate_fluxes (solver.c:66-82, 146-279): V = float2 is a PAIR of groups on packed
+// FP32 instructions, V = float one group on scalar instructions.  Returns the tallies.
+// (c0, d, e) are the fit coefficients (c0, c1, c2) of the segment's stencil, computed once per sweep by
+// fit_coefficients_kernel exactly as solver.c:74-76 writes them, so that solver.c:79-81 is
+//   q0 = c0 + a1 d + a2 e,  q1 mu = b1 d + b2 e,  q2 mu^2 = b3 e
+// with the per-segment scalars a1 = zin, a2 = zin^2, b1 = mu, b2 = 2 mu zin, b3 = mu^2.
+// The rest is the reference's formulas, regrouped so that every factor that does not depend on the
+// group is a per-segment scalar and every division is a multiplication by MUFU.RCP(sigT):
 //   in  = [ q0 tau + (sigT psi - q0) E + q2 mu^2 C3 / sigT^2 ] / sigT^2 + q1 mu R
 //   out = q0 E / sigT + q1 mu (tau - E) / sigT^2 + q2 mu^2 R + psi (1 - E)
 //   R   = tau (tau - 2) + 2 E / sigT^3          (solver.c:175-176 as parenthesised there)
 //   C3  = [tau (tau (tau - 3) + 6) - 6 E] / 3
-template <int MODE, bool HI>
-__device__ __forceinline__ float2 attenuate_pair(float2 y1, float2 y2, float2 y3, float2 sigT, float2 &psi,
-                                                 const SegmentScalars &k, const TableConsts &tc)
+template <int MODE, typename V>
+__device__ __forceinline__ V attenuate_groups(V c0, V d, V e, V sigT, V &psi, const SegmentScalars &k,
+                                              const TableConsts &tc)
 {
-    const float2 d = sub2(y1, y3);
-    const float2 e = fma2(bc(-2.f), y2, add2(y1, y3));
-    const float2 q0 = fma2(bc(k.a2), e, fma2(bc(k.a1), d, y2));
-    const float2 q1m = fma2(bc(k.b2), e, mul2(bc(k.b1), d));   // q1 * mu
-    const float2 q2m = mul2(bc(k.b3), e);                      // q2 * mu^2
-    const float2 tau = mul2(sigT, bc(k.ds));
-    float2 E, D;
-    one_minus_exp2<MODE, HI>(tau, tc, E, D);
-    float2 r1;
-    r1.x = rcp_approx(sigT.x);
-    r1.y = HI ? rcp_approx(sigT.y) : 0.0f;
-    const float2 r2 = mul2(r1, r1);
-    const float2 Er1 = mul2(E, r1);
-    const float2 reuse = fma2(bc(2.f), mul2(Er1, r2), mul2(tau, add2(tau, bc(-2.f))));
-    const float2 A = fma2(q0, tau, mul2(fma2(sigT, psi, neg2(q0)), E));
-    const float2 c3 = fma2(bc(-2.f), E, mul2(tau, fma2(tau, fma2(tau, bc(1.f / 3.f), bc(-1.f)), bc(2.f))));
-    const float2 X = fma2(mul2(q2m, r2), c3, A);
-    const float2 in = fma2(X, r2, mul2(q1m, reuse));
-    float2 out = mul2(q0, Er1);
+    const V q0 = fma2(splat<V>(k.a2), e, fma2(splat<V>(k.a1), d, c0));
+    const V q1m = fma2(splat<V>(k.b2), e, mul2(splat<V>(k.b1), d));   // q1 * mu
+    const V q2m = mul2(splat<V>(k.b3), e);                            // q2 * mu^2
+    const V tau = mul2(sigT, splat<V>(k.ds));
+    V E, D;
+    one_minus_exp2<MODE>(tau, tc, E, D);
+    const V r1 = rcp_groups(sigT);
+    const V r2 = mul2(r1, r1);
+    const V Er1 = mul2(E, r1);
+    const V reuse = fma2(splat<V>(2.f), mul2(Er1, r2), mul2(tau, add2(tau, splat<V>(-2.f))));
+    const V A = fma2(q0, tau, mul2(fma2(sigT, psi, neg2(q0)), E));
+    const V c3 = fma2(splat<V>(-2.f), E,
+                      mul2(tau, fma2(tau, fma2(tau, splat<V>(1.f / 3.f), splat<V>(-1.f)), splat<V>(2.f))));
+    const V X = fma2(mul2(q2m, r2), c3, A);
+    const V in = fma2(X, r2, mul2(q1m, reuse));
+    // table modes: out + psi (1 - E) as (psi + q0 E / sigT + ...) - psi E, so D = 1 - E is never formed;
+    // SFU mode has D = exp(-tau) from the MUFU already
+    V out = MODE == 2 ? mul2(q0, Er1) : fma2(q0, Er1, psi);
     out = fma2(mul2(q1m, r2), sub2(tau, E), out);
     out = fma2(q2m, reuse, out);
-    psi = fma2(psi, D, out);
-    return mul2(bc(k.weight), in);
+    psi = MODE == 2 ? fma2(psi, D, out) : fma2(neg2(psi), E, out);
+    return mul2(splat<V>(k.weight), in);
 }
 
 // one energy group of attenuate_FSR_fluxes (solver.c:1104-1115); scalar: 11 FLOP, not worth packing
@@ -170,12 +210,36 @@ __device__ __forceinline__ float attenuate_flat(float src, float sigT, float &ps
                                                 const TableConsts &tc)
 {
     const float tau = sigT * k.ds;
-    float2 E, D;
-    one_minus_exp2<MODE, false>(make_float2(tau, 0.f), tc, E, D);
+    float E, D;
+    one_minus_exp2<MODE>(tau, tc, E, D);
     const float q = __fdiv_rn(src, sigT);   // flat source: the difference psi - q cancels, keep the division exact
-    const float dpsi = (psi - q) * E.x;
+    const float dpsi = (psi - q) * E;
     psi -= dpsi;
     return k.weight * dpsi;
+}
+
+// The quadratic "fitting" of solver.c:74-76 for every stencil of every source region, written exactly as the
+// reference writes it (IEEE divisions, same order of additions): stencil r0 of region i fits source rows
+// r0, r0+1, r0+2 and is what fine intervals r0+1 (and, at the edges, 0 and fai-1: solver.c:55-112) use.
+// coef[i][r0][0..2][pitch] = (c0, c1, c2).  N * (fai-2) * pitch threads of work, once per sweep.
+__global__ void fit_coefficients_kernel(const float *__restrict__ fine_source, float *__restrict__ coef,
+                                        long long n_regions, int fai, int pitch, float dz)
+{
+    const int S = fai - 2;
+    const long long cells = n_regions * S * pitch;
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= cells) return;
+    const int g = (int)(e % pitch);
+    const long long rs = e / pitch;
+    const int r0 = (int)(rs % S);
+    const long long i = rs / S;
+    const float *y = fine_source + ((size_t)i * fai + r0) * pitch + g;
+    const float y1 = y[0], y2 = y[pitch], y3 = y[2 * pitch];
+    float *c = coef + (size_t)rs * 3 * pitch + g;
+    const float two_dz = __fmul_rn(2.f, dz);
+    c[0] = y2;
+    c[pitch] = __fdiv_rn(__fadd_rn(y1, -y3), two_dz);
+    c[2 * pitch] = __fdiv_rn(__fadd_rn(__fadd_rn(y1, -__fmul_rn(2.f, y2)), y3), __fmul_rn(two_dz, dz));
 }
 
 // fine_flux is only ever reduced into by this kernel (never read), so the reductions carry no
@@ -234,10 +298,10 @@ __global__ void __launch_bounds__(128, MOC_ATT_MIN_BLOCKS) attenuate_kernel(cons
         float w0 = __fmul_rn(a.p_weight[t], a.az_weight[i]);   // solver.c:49
         if (FLAT) w0 = __fmul_rn(w0, mu);                      // solver.c:1064
         sc.weight = w0;
-        sc.b1 = mu * a.inv_2dz;
-        sc.b3 = mu * mu * a.inv_2dz2;
+        sc.b1 = mu;
+        sc.b3 = mu * mu;
     }
-    const float two_mu_c = 2.f * mu * a.inv_2dz2;
+    const float two_mu = 2.f * mu;
     unsigned int longest = n_rec;
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {
@@ -276,10 +340,11 @@ __global__ void __launch_bounds__(128, MOC_ATT_MIN_BLOCKS) attenuate_kernel(cons
         nxt_zin = __ldg(rec_zin + lit * Zs);
         nxt_code = __ldg(rec_code + lit * Zs);
     }
-    const float *const src_q = a.fine_source + 4 * lit;          // this lane's quads
+    const float *const src_base = FLAT ? a.fine_source : a.coef;   // quadratic source: fit coefficients
+    const float *const src_q = src_base + 4 * lit;               // this lane's quads
     const float *const sig_q = a.sigT + 4 * lit;
     float *const flx_q = a.fine_flux + 4 * lit;
-    const float *const src_s = a.fine_source + g_tail + lit;     // this lane's single groups
+    const float *const src_s = src_base + g_tail + lit;          // this lane's single groups
     const float *const sig_s = a.sigT + g_tail + lit;
     float *const flx_s = a.fine_flux + g_tail + lit;
 
@@ -299,16 +364,19 @@ __global__ void __launch_bounds__(128, MOC_ATT_MIN_BLOCKS) attenuate_kernel(cons
         const uint32_t code = __shfl_sync(0xffffffffu, cur_code, slot, L);
         if (sgm < n_rec) {
             sc.ds = seg_ds;
-            sc.a1 = zin * a.inv_2dz;
-            sc.a2 = zin * zin * a.inv_2dz2;
-            sc.b2 = two_mu_c * zin;
+            sc.a1 = zin;
+            sc.a2 = zin * zin;
+            sc.b2 = two_mu * zin;
             const uint32_t qsr = code & 0xffffffu;
             const uint32_t r0 = (code >> 24) & 63u;
             const uint32_t which = code >> 30;
             // element offsets inside the source slab (< 2^32, checked by moc_create)
-            const uint32_t o_src = (qsr * a.fai + r0) * (uint32_t)W;
+            // quadratic source: o_src addresses the (c0, c1, c2) rows of stencil r0 in the coefficient slab;
+            // flat source: the source row itself (r0 = fine interval)
+            const uint32_t o_row = (qsr * a.fai + r0) * (uint32_t)W;
+            const uint32_t o_src = FLAT ? o_row : (qsr * a.coef_stencils + r0) * 3u * (uint32_t)W;
             const uint32_t o_sig = qsr * (uint32_t)W;
-            const uint32_t o_flx = o_src + which * (uint32_t)W;
+            const uint32_t o_flx = o_row + which * (uint32_t)W;
 #pragma unroll
             for (int v = 0; v < NV4; v++) {
                 const int g = 4 * (lit + L * v);
@@ -322,16 +390,16 @@ __global__ void __launch_bounds__(128, MOC_ATT_MIN_BLOCKS) attenuate_kernel(cons
                         tally.z = attenuate_flat<MODE>(y.z, s4.z, psi4[v].z, sc, tc);
                         tally.w = attenuate_flat<MODE>(y.w, s4.w, psi4[v].w, sc, tc);
                     } else {
-                        const float4 y1 = __ldg(reinterpret_cast<const float4 *>(src_q + o_src + 4 * L * v));
-                        const float4 y2 = __ldg(reinterpret_cast<const float4 *>(src_q + o_src + W + 4 * L * v));
-                        const float4 y3 = __ldg(reinterpret_cast<const float4 *>(src_q + o_src + 2 * W + 4 * L * v));
+                        const float4 k0 = __ldg(reinterpret_cast<const float4 *>(src_q + o_src + 4 * L * v));
+                        const float4 k1 = __ldg(reinterpret_cast<const float4 *>(src_q + o_src + W + 4 * L * v));
+                        const float4 k2 = __ldg(reinterpret_cast<const float4 *>(src_q + o_src + 2 * W + 4 * L * v));
                         float2 plo = make_float2(psi4[v].x, psi4[v].y), phi = make_float2(psi4[v].z, psi4[v].w);
-                        const float2 tlo = attenuate_pair<MODE, true>(make_float2(y1.x, y1.y), make_float2(y2.x, y2.y),
-                                                                      make_float2(y3.x, y3.y), make_float2(s4.x, s4.y),
-                                                                      plo, sc, tc);
-                        const float2 thi = attenuate_pair<MODE, true>(make_float2(y1.z, y1.w), make_float2(y2.z, y2.w),
-                                                                      make_float2(y3.z, y3.w), make_float2(s4.z, s4.w),
-                                                                      phi, sc, tc);
+                        const float2 tlo = attenuate_groups<MODE>(
+                            make_float2(k0.x, k0.y), make_float2(k1.x, k1.y), make_float2(k2.x, k2.y),
+                            make_float2(s4.x, s4.y), plo, sc, tc);
+                        const float2 thi = attenuate_groups<MODE>(
+                            make_float2(k0.z, k0.w), make_float2(k1.z, k1.w), make_float2(k2.z, k2.w),
+                            make_float2(s4.z, s4.w), phi, sc, tc);
                         psi4[v] = make_float4(plo.x, plo.y, phi.x, phi.y);
                         tally = make_float4(tlo.x, tlo.y, thi.x, thi.y);
                     }
@@ -347,12 +415,9 @@ __global__ void __launch_bounds__(128, MOC_ATT_MIN_BLOCKS) attenuate_kernel(cons
                     if (FLAT) {
                         tally = attenuate_flat<MODE>(__ldg(src_s + o_src + L * s), s1, psi1[s], sc, tc);
                     } else {
-                        float2 p = make_float2(psi1[s], 0.f);
-                        const float2 tl = attenuate_pair<MODE, false>(
-                            make_float2(__ldg(src_s + o_src + L * s), 0.f), make_float2(__ldg(src_s + o_src + W + L * s), 0.f),
-                            make_float2(__ldg(src_s + o_src + 2 * W + L * s), 0.f), make_float2(s1, 0.f), p, sc, tc);
-                        psi1[s] = p.x;
-                        tally = tl.x;
+                        // the tail group runs on scalar FFMA/FMUL/FADD, not on a half-empty pair
+                        tally = attenuate_groups<MODE>(__ldg(src_s + o_src + L * s), __ldg(src_s + o_src + W + L * s),
+                                                       __ldg(src_s + o_src + 2 * W + L * s), s1, psi1[s], sc, tc);
                     }
                     red_add(flx_s + o_flx + L * s, tally);
                 }

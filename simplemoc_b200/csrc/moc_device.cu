@@ -106,6 +106,7 @@ struct DeviceBuffers {
     TrackImage *track_image = nullptr;   // only for the drop-in path
     // sources
     float *src = nullptr, *xs = nullptr, *scatter = nullptr, *vol = nullptr, *table = nullptr;
+    float *coef = nullptr;               // quadratic fit coefficients of every stencil, rebuilt before each sweep
     int *xs_index = nullptr;
     // sweep scratch
     uint32_t *seg_count = nullptr, *pair_max = nullptr, *rec_code = nullptr;
@@ -192,7 +193,7 @@ static int dev_alloc(T **p, size_t count)
 static void free_buffers(DeviceBuffers &d)
 {
     void *all[] = {d.az_weight, d.n_seg, d.seg_start, d.seg_len, d.cos_p, d.sin_p, d.mu, d.p_weight,
-                   d.z_height, d.psi, d.track_image, d.src, d.xs, d.scatter, d.vol, d.table,
+                   d.z_height, d.psi, d.track_image, d.src, d.coef, d.xs, d.scatter, d.vol, d.table,
                    d.xs_index, d.seg_count, d.pair_max, d.rec_code, d.pair_count, d.pair_base, d.rec_base,
                    d.digest, d.rec_ds, d.rec_zin, d.per_region_a, d.per_region_b, d.per_fine,
                    d.scalars, d.leakage};
@@ -517,6 +518,11 @@ static int create_common(const Input *I, const Params *P, int device, int source
         moc_set_error("source slab has more than 2^32 elements (the attenuation kernel indexes it with 32 bits)");
         return MOC_EINVAL;
     }
+    if (I->axial_exp == 2 && 3.0 * (double)(I->fai - 2) * (double)I->n_source_regions_per_node *
+                                 (double)((I->n_egroups + 31) / 32 * 32) >= 4294967296.0) {
+        moc_set_error("fit-coefficient slab has more than 2^32 elements (the attenuation kernel indexes it with 32 bits)");
+        return MOC_EINVAL;
+    }
     if (!synthetic && (rc = inspect_layout(I, P, source_stride, L))) return rc;
     CUDA_TRY(cudaSetDevice(device));
     moc_handle *h = new moc_handle();
@@ -557,6 +563,7 @@ static int create_common(const Input *I, const Params *P, int device, int source
     if ((rc = dev_alloc(&h->d.psi, 2 * T3 * G))) return fail(rc);
     if ((rc = dev_alloc(&h->d.src, (2 * F + 1) * N * (size_t)h->Gp))) return fail(rc);
     cudaMemsetAsync(h->d.src, 0, sizeof(float) * (2 * F + 1) * N * (size_t)h->Gp, h->stream);   // padding columns stay 0
+    if (I->axial_exp == 2 && (rc = dev_alloc(&h->d.coef, 3 * (size_t)(F - 2) * N * (size_t)h->Gp))) return fail(rc);
     if ((rc = dev_alloc(&h->d.seg_count, T3))) return fail(rc);
     if ((rc = dev_alloc(&h->d.pair_count, pairs))) return fail(rc);
     if ((rc = dev_alloc(&h->d.pair_base, pairs + 1))) return fail(rc);
@@ -606,7 +613,7 @@ extern "C" int moc_create(const Input *I, const Params *P, int device, moc_handl
 // device fills them in parallel -- bit-identical to moc_build_tracks + moc_create
 // (tests/test_gpu_parity.py::test_device_construction_is_bit_identical).  The 2D tracks, the polar
 // angles and the exponential table stay on the host: they are small and depend on the host libm.
-extern "C" int moc_create_synthetic(const Input *I, unsigned long long seed, int device, moc_handle **out,
+extern "C" int moc_create_synthetic(Input *I, unsigned long long seed, int device, moc_handle **out,
                                     unsigned long long *rand_calls)
 {
     if (!I || !out) {
@@ -1090,6 +1097,8 @@ static int sweep_core(moc_handle *h, long *segments_processed, const HostLayout 
     a.mu = h->d.mu;
     a.psi = h->d.psi;
     a.fine_source = h->d.src;
+    a.coef = h->d.coef;
+    a.coef_stencils = h->F - 2;
     a.fine_flux = h->d.src + (size_t)h->N * h->F * h->Gp;
     a.sigT = h->d.src + (size_t)2 * h->N * h->F * h->Gp;
     a.pitch = h->Gp;
@@ -1103,10 +1112,13 @@ static int sweep_core(moc_handle *h, long *segments_processed, const HostLayout 
     a.Z = h->Z;
     a.G = h->G;
     a.fai = h->F;
-    {
-        const float dz = w.dz_fine;
-        a.inv_2dz = 1.0f / (2.f * dz);
-        a.inv_2dz2 = 1.0f / (2.f * dz * dz);
+
+    if (h->d.coef) {
+        // the source only changes between sweeps (update_sources, uploads): fit every stencil once
+        const long long cells = h->N * (h->F - 2) * (long long)h->Gp;
+        fit_coefficients_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, h->stream>>>(
+            h->d.src, h->d.coef, h->N, h->F, h->Gp, w.dz_fine);
+        h->launch_count++;
     }
 
     // three events per batch: before the fill, between fill and attenuation, after

@@ -296,49 +296,222 @@ static int make_exp_table(Table *tab, float precision, float maxVal)
     return MOC_OK;
 }
 
-/* The cheap, libm-dependent part of build_tracks(): 2D tracks (tracks.c:4-58), polar angles
- * (tracks.c:159-168), the exponential table (utils.c:48-78), the leakage cell -- plus the stream
- * positions of every later block of draws.  Params.tracks and Params.sources stay NULL: the
- * device fills those arrays itself (moc_create_synthetic). */
-int moc_build_tracks_2d(const Input *in, uint64_t seed, Params *out, moc_draw_layout *layout)
+/* ---- OpenMOC track files (tracks.c:170-323, the -d option) ----
+ * On-disk layout, as that reader consumes it (native endianness, no padding):
+ *   int    string_length;  char geometry[string_length];
+ *   int    n_azimuthal;    double spacing;
+ *   int    num_tracks[n_azimuthal], num_x[n_azimuthal], num_y[n_azimuthal];
+ *   double azim_weights[n_azimuthal];
+ *   per track (azimuthal angle major):  double x0, y0, x1, y1, phi;  int azim_angle_index;
+ *                                       int num_segments;
+ *     per segment:  double length;  int material_id;  int region_id;  (+ 2 ints if cmfd)
+ * What the reference keeps: n_azimuthal, (float)spacing -> radial_ray_sep, per track the segment
+ * count, per segment (float)length and region_id -> source_id; it draws az_weight = urand() per
+ * track (tracks.c:283), recomputes segments_per_track = total / ntracks_2D (integer division,
+ * tracks.c:311) and ntracks.  Everything else in the file is skipped.  Unlike the reference, a
+ * missing, truncated or implausible file is an error (MOC_EIO), not undefined behaviour. */
+typedef struct {
+    FILE *f;
+    const char *name;
+    int failed;
+} track_reader;
+
+static void rd(track_reader *r, void *dst, size_t size, size_t count)
 {
-    if (in->load_tracks || in->ntracks_2D <= 0 || in->z_stacked <= 0 || in->n_polar_angles <= 0 ||
-        in->n_egroups <= 0 || in->fai <= 0 || in->n_source_regions_per_node < 8) {
-        moc_set_error("degenerate problem: T2=%ld Z=%d P=%d G=%d fai=%d N=%ld (need N >= 8, no track file)",
-                      in->ntracks_2D, in->z_stacked, in->n_polar_angles, in->n_egroups,
-                      in->fai, in->n_source_regions_per_node);
+    if (r->failed || count == 0) return;
+    if (fread(dst, size, count, r->f) != count) r->failed = 1;
+}
+
+static void rd_skip(track_reader *r, long bytes)
+{
+    if (r->failed) return;
+    if (fseek(r->f, bytes, SEEK_CUR) != 0) r->failed = 1;
+}
+
+int moc_load_openmoc_tracks(const char *fname, int cmfd, Input *in, uint64_t seed, uint64_t az_weight_at,
+                            Track2D **tracks_out, long *total_segments_out)
+{
+    if (!fname || !in || !tracks_out) {
+        moc_set_error("moc_load_openmoc_tracks: null argument");
         return MOC_EINVAL;
     }
-    const long T2 = in->ntracks_2D, T3 = in->ntracks, N = in->n_source_regions_per_node;
-    const long X = N / 8;
-    const int P = in->n_polar_angles, G = in->n_egroups, F = in->fai;
-    memset(out, 0, sizeof *out);
-    moc_draw_layout at;
-    at.az_weight = 0;
-    at.n_segments = at.az_weight + (uint64_t)T2;
-    at.seg_length = at.n_segments + 2 * (uint64_t)T2;
+    track_reader r = { fopen(fname, "rb"), fname, 0 };
+    if (!r.f) {
+        moc_set_error("cannot open track file '%s'", fname);
+        return MOC_EIO;
+    }
+    fseek(r.f, 0, SEEK_END);
+    const long file_bytes = ftell(r.f);
+    fseek(r.f, 0, SEEK_SET);
+    int rc = MOC_EIO;
+    Track2D *t2 = NULL;
+    Segment *segs = NULL;
+    int *per_angle = NULL;
+
+    int string_length = 0, n_azim = 0;
+    double spacing = 0;
+    rd(&r, &string_length, sizeof(int), 1);
+    if (r.failed || string_length < 0 || string_length > file_bytes) {
+        moc_set_error("track file '%s': bad geometry-string length %d", fname, string_length);
+        goto done;
+    }
+    rd_skip(&r, string_length);
+    rd(&r, &n_azim, sizeof(int), 1);
+    rd(&r, &spacing, sizeof(double), 1);
+    if (r.failed || n_azim <= 0 || (long)n_azim * 20 > file_bytes) {
+        moc_set_error("track file '%s': bad number of azimuthal angles %d", fname, n_azim);
+        goto done;
+    }
+    per_angle = (int *)malloc(sizeof(int) * (size_t)n_azim);
+    if (!per_angle) { rc = MOC_ENOMEM; goto done; }
+    rd(&r, per_angle, sizeof(int), (size_t)n_azim);
+    rd_skip(&r, (long)n_azim * (2 * (long)sizeof(int) + (long)sizeof(double)));   /* num_x, num_y, azim_weights */
+    long T2 = 0;
+    for (int a = 0; a < n_azim && !r.failed; a++) {
+        if (per_angle[a] < 0) r.failed = 1;
+        T2 += per_angle[a];
+    }
+    /* a track takes at least 5 doubles + 2 ints on disk */
+    if (r.failed || T2 <= 0 || T2 * 48 > file_bytes) {
+        moc_set_error("track file '%s': bad track counts (%ld tracks in a %ld-byte file)", fname, T2, file_bytes);
+        goto done;
+    }
+
+    /* pass 1: segment total (tracks.c:225-250) */
+    const long body = ftell(r.f);
+    const long seg_bytes = (long)sizeof(double) + 2 * (long)sizeof(int) + (cmfd ? 2 * (long)sizeof(int) : 0);
+    long total = 0;
+    for (long u = 0; u < T2 && !r.failed; u++) {
+        int n = 0;
+        rd_skip(&r, 5 * (long)sizeof(double) + (long)sizeof(int));
+        rd(&r, &n, sizeof(int), 1);
+        if (n < 0 || (long)n * seg_bytes > file_bytes) r.failed = 1;
+        total += n;
+        rd_skip(&r, (long)n * seg_bytes);
+    }
+    if (r.failed || ftell(r.f) > file_bytes) {
+        moc_set_error("track file '%s' is truncated or corrupt (segment counts run past its %ld bytes)", fname, file_bytes);
+        goto done;
+    }
+
+    /* pass 2: the data (tracks.c:259-308) */
+    t2 = (Track2D *)calloc((size_t)T2, sizeof(Track2D));
+    segs = (Segment *)calloc((size_t)(total > 0 ? total : 1), sizeof(Segment));
+    if (!t2 || !segs) { rc = MOC_ENOMEM; goto done; }
+    fseek(r.f, body, SEEK_SET);
+    long first = 0;
+    for (long u = 0; u < T2 && !r.failed; u++) {
+        int n = 0;
+        rd_skip(&r, 5 * (long)sizeof(double) + (long)sizeof(int));
+        rd(&r, &n, sizeof(int), 1);
+        t2[u].n_segments = n;
+        t2[u].segments = segs + first;
+        t2[u].az_weight = moc_urand(seed, az_weight_at + (uint64_t)u);     /* tracks.c:283 */
+        for (int sgm = 0; sgm < n && !r.failed; sgm++) {
+            double length = 0;
+            int ids[2] = { 0, 0 };                                       /* material_id, region_id */
+            rd(&r, &length, sizeof(double), 1);
+            rd(&r, ids, sizeof(int), 2);
+            if (cmfd) rd_skip(&r, 2 * (long)sizeof(int));
+            segs[first + sgm].length = (float)length;
+            segs[first + sgm].source_id = (long)ids[1];
+        }
+        first += n;
+    }
+    if (r.failed) {
+        moc_set_error("track file '%s': read error in the track data", fname);
+        goto done;
+    }
+    in->n_azimuthal = n_azim;
+    in->radial_ray_sep = (float)spacing;
+    in->ntracks_2D = T2;
+    in->segments_per_track = total / T2;
+    in->ntracks = T2 * in->n_polar_angles * in->z_stacked;
+    *tracks_out = t2;
+    if (total_segments_out) *total_segments_out = total;
+    t2 = NULL;
+    segs = NULL;
+    rc = MOC_OK;
+done:
+    free(per_angle);
+    free(t2);
+    free(segs);
+    fclose(r.f);
+    return rc;
+}
+
+/* 2D tracks of build_tracks() (init.c:119-125): from the track file when -d was given, else the
+ * synthetic ones of tracks.c:4-58.  Fills the first three stream positions of *at and at->p_weight. */
+static int make_tracks_2d(Input *in, uint64_t seed, moc_draw_layout *at, Track2D **out)
+{
+    at->az_weight = 0;
+    if (in->load_tracks) {
+        long total = 0;
+        int rc = moc_load_openmoc_tracks(in->track_file, 0, in, seed, at->az_weight, out, &total);
+        if (rc) return rc;
+        /* one draw per track and nothing else (tracks.c:283) */
+        at->n_segments = at->seg_length = at->p_weight = at->az_weight + (uint64_t)in->ntracks_2D;
+        return MOC_OK;
+    }
+    const long T2 = in->ntracks_2D;
+    at->n_segments = at->az_weight + (uint64_t)T2;
+    at->seg_length = at->n_segments + 2 * (uint64_t)T2;
     Track2D *t2 = (Track2D *)calloc((size_t)T2, sizeof(Track2D));
     if (!t2) return MOC_ENOMEM;
     long total_segments = 0;
     for (long i = 0; i < T2; i++) {
-        t2[i].az_weight = moc_urand(seed, at.az_weight + (uint64_t)i);
-        t2[i].n_segments = normal_draw(seed, at.n_segments + 2 * (uint64_t)i,
+        t2[i].az_weight = moc_urand(seed, at->az_weight + (uint64_t)i);
+        t2[i].n_segments = normal_draw(seed, at->n_segments + 2 * (uint64_t)i,
                                        in->segments_per_track, sqrt(in->segments_per_track));
-        if (t2[i].n_segments < 0) t2[i].n_segments = 0;
+        if (t2[i].n_segments < 0) t2[i].n_segments = 0;   /* cannot index a negative count */
         total_segments += t2[i].n_segments;
     }
     Segment *segs = (Segment *)calloc((size_t)(total_segments > 0 ? total_segments : 1), sizeof(Segment));
-    if (!segs) return MOC_ENOMEM;
+    if (!segs) {
+        free(t2);
+        return MOC_ENOMEM;
+    }
     long first = 0;
     for (long i = 0; i < T2; i++) {
         t2[i].segments = segs + first;
         for (long n = 0; n < t2[i].n_segments; n++)
-            segs[first + n].length = moc_urand(seed, at.seg_length + (uint64_t)(first + n))
+            segs[first + n].length = moc_urand(seed, at->seg_length + (uint64_t)(first + n))
                                      * in->assembly_width / t2[i].n_segments;
         first += t2[i].n_segments;
     }
+    at->p_weight = at->seg_length + (uint64_t)total_segments;
+    *out = t2;
+    return MOC_OK;
+}
+
+static int check_sizes(const Input *in)
+{
+    if ((!in->load_tracks && in->ntracks_2D <= 0) || in->z_stacked <= 0 || in->n_polar_angles <= 0 ||
+        in->n_egroups <= 0 || in->fai <= 0 || in->n_source_regions_per_node < 8) {
+        moc_set_error("degenerate problem: T2=%ld Z=%d P=%d G=%d fai=%d N=%ld (need N >= 8)",
+                      in->ntracks_2D, in->z_stacked, in->n_polar_angles, in->n_egroups,
+                      in->fai, in->n_source_regions_per_node);
+        return MOC_EINVAL;
+    }
+    return MOC_OK;
+}
+
+/* The cheap, libm-dependent part of build_tracks(): 2D tracks (tracks.c:4-58), polar angles
+ * (tracks.c:159-168), the exponential table (utils.c:48-78), the leakage cell -- plus the stream
+ * positions of every later block of draws.  Params.tracks and Params.sources stay NULL: the
+ * device fills those arrays itself (moc_create_synthetic). */
+int moc_build_tracks_2d(Input *in, uint64_t seed, Params *out, moc_draw_layout *layout)
+{
+    int rc0 = check_sizes(in);
+    if (rc0) return rc0;
+    memset(out, 0, sizeof *out);
+    moc_draw_layout at;
+    Track2D *t2 = NULL;
+    if ((rc0 = make_tracks_2d(in, seed, &at, &t2))) return rc0;
+    const long T3 = in->ntracks, N = in->n_source_regions_per_node;
+    const long X = N / 8;
+    const int P = in->n_polar_angles, G = in->n_egroups, F = in->fai;
     out->tracks_2D = t2;
-    at.p_weight = at.seg_length + (uint64_t)total_segments;
     float *polar = (float *)malloc(sizeof(float) * (size_t)P);
     if (!polar) return MOC_ENOMEM;
     for (int j = 0; j < P; j++) polar[j] = M_PI * (j + 0.5) / P;
@@ -357,55 +530,20 @@ int moc_build_tracks_2d(const Input *in, uint64_t seed, Params *out, moc_draw_la
 }
 
 /* init.c:106-159 = tracks.c:4-58 + tracks.c:75-168 + source.c:4-214 + utils.c:48-78 */
-int moc_build_tracks(const Input *in, uint64_t seed, Params *out, uint64_t *rand_calls)
+int moc_build_tracks(Input *in, uint64_t seed, Params *out, uint64_t *rand_calls)
 {
-    if (in->load_tracks) {
-        moc_set_error("OpenMOC track files (-d, reference tracks.c:170-323) are out of scope: "
-                      "no sample file ships with the reference");
-        return MOC_EINVAL;
-    }
-    if (in->ntracks_2D <= 0 || in->z_stacked <= 0 || in->n_polar_angles <= 0 ||
-        in->n_egroups <= 0 || in->fai <= 0 || in->n_source_regions_per_node < 8) {
-        moc_set_error("degenerate problem: T2=%ld Z=%d P=%d G=%d fai=%d N=%ld (need N >= 8)",
-                      in->ntracks_2D, in->z_stacked, in->n_polar_angles, in->n_egroups,
-                      in->fai, in->n_source_regions_per_node);
-        return MOC_EINVAL;
-    }
+    int rc0 = check_sizes(in);
+    if (rc0) return rc0;
+    memset(out, 0, sizeof *out);
+
+    /* ---- 2D tracks (the track file may change ntracks_2D, ntracks, n_azimuthal, ...) ---- */
+    moc_draw_layout at;
+    Track2D *t2 = NULL;
+    if ((rc0 = make_tracks_2d(in, seed, &at, &t2))) return rc0;
     const long T2 = in->ntracks_2D, T3 = in->ntracks, N = in->n_source_regions_per_node;
     const long X = N / 8;                                   /* source.c:12 */
     const int P = in->n_polar_angles, Z = in->z_stacked, G = in->n_egroups, F = in->fai;
-    memset(out, 0, sizeof *out);
-
-    moc_draw_layout at;
-    at.az_weight = 0;
-    at.n_segments = at.az_weight + (uint64_t)T2;
-    at.seg_length = at.n_segments + 2 * (uint64_t)T2;
-
-    /* ---- 2D tracks ---- */
-    Track2D *t2 = (Track2D *)calloc((size_t)T2, sizeof(Track2D));
-    if (!t2) return MOC_ENOMEM;
-    long total_segments = 0;
-    for (long i = 0; i < T2; i++) {
-        t2[i].az_weight = moc_urand(seed, at.az_weight + (uint64_t)i);
-        t2[i].n_segments = normal_draw(seed, at.n_segments + 2 * (uint64_t)i,
-                                       in->segments_per_track, sqrt(in->segments_per_track));
-        if (t2[i].n_segments < 0) t2[i].n_segments = 0;   /* cannot index a negative count */
-        total_segments += t2[i].n_segments;
-    }
-    Segment *segs = (Segment *)calloc((size_t)(total_segments > 0 ? total_segments : 1), sizeof(Segment));
-    if (!segs) return MOC_ENOMEM;
-    {
-        long first = 0;
-        for (long i = 0; i < T2; i++) {
-            t2[i].segments = segs + first;
-            for (long n = 0; n < t2[i].n_segments; n++)
-                segs[first + n].length = moc_urand(seed, at.seg_length + (uint64_t)(first + n))
-                                         * in->assembly_width / t2[i].n_segments;
-            first += t2[i].n_segments;
-        }
-    }
     out->tracks_2D = t2;
-    at.p_weight = at.seg_length + (uint64_t)total_segments;
 
     /* ---- 3D tracks: [i][j][k] views over one Track array and one flux slab ---- */
     Track ***by_i = (Track ***)malloc(sizeof(Track **) * (size_t)T2);

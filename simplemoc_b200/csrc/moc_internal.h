@@ -37,7 +37,7 @@ typedef struct {
 } moc_draw_layout;
 
 /* 2D tracks, polar angles, exponential table and the draw layout only (moc_host.c) */
-int moc_build_tracks_2d(const Input *in, uint64_t seed, Params *out, moc_draw_layout *layout);
+int moc_build_tracks_2d(Input *in, uint64_t seed, Params *out, moc_draw_layout *layout);
 
 #ifdef __cplusplus
 }

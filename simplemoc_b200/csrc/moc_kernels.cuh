@@ -89,6 +89,8 @@ struct AttenuateParams {
     const float *mu;                  // [P] (float)cos(polar[j])
     float *psi;                       // [T3][2][G]
     const float *fine_source;         // [N][fai][pitch]   rows padded to 128 bytes (pitch = G rounded up to 32)
+    const float *coef;                // [N][coef_stencils][3][pitch]  (c0, c1, c2) of solver.c:74-76 per stencil
+    int coef_stencils;                // fai - 2: stencil r0 covers source rows r0 .. r0+2
     float *fine_flux;                 // [N][fai][pitch]
     const float *sigT;                // [N][pitch]
     int pitch;
@@ -97,7 +99,6 @@ struct AttenuateParams {
     int table_n;
     long long first_track, end_track; // tracks of this batch
     int P, Z, G, fai;
-    float inv_2dz, inv_2dz2;          // 1/(2 dz), 1/(2 dz dz) of solver.c:75-76
 };
 
 // record code: | which:2 | r0:6 | qsr:24 |   (stencil rows r0..r0+2, tally row r0+which)

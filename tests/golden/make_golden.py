@@ -28,12 +28,20 @@ def sha(a):
     return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
 
 
-def run_case(name, variant=""):
-    r = RefCase(CASES[name], seed=SEEDS[name], variant=variant)
+TRACK_FILE = os.path.join(HERE, "tracks_44.bin")   # tests/golden/make_track_file.py
+
+
+def run_case(name, variant="", track_file=None):
+    r = RefCase(CASES[name], seed=SEEDS[name], variant=variant, track_file=track_file)
     out = {"seed": SEEDS[name], "values": CASES[name], "init_rand_calls": int(r.init_rand_calls)}
     I = r.I
     out["derived"] = {"ntracks_2D": I.ntracks_2D, "z_stacked": I.z_stacked, "ntracks": I.ntracks,
                       "n_source_regions_per_node": I.n_source_regions_per_node}
+    if track_file:
+        # what load_OpenMOC_tracks (tracks.c:170-323) changes in the Input
+        out["track_file"] = os.path.basename(track_file)
+        out["derived"].update({"n_azimuthal": I.n_azimuthal, "radial_ray_sep": float(I.radial_ray_sep),
+                               "segments_per_track": I.segments_per_track})
     az, ns, ln = r.tracks_2D()
     pw, zh = r.tracks()
     idx, vol = r.source_meta()
@@ -61,7 +69,9 @@ def main():
               "reference": "ANL-CESAR/SimpleMOC v4 sources, unmodified, -O2 -ffp-contract=off, serial, "
                            "rand()=moc_rand31(seed, call index) (oracle/ref_shim.c)",
               "table": {n: run_case(n) for n in CASES},
-              "expf": {n: run_case(n, "_expf") for n in ("tiny", "mini104")}}
+              "expf": {n: run_case(n, "_expf") for n in ("tiny", "mini104")},
+              # 2D tracks read by the reference's own load_OpenMOC_tracks from tests/golden/tracks_44.bin
+              "tracks": {n: run_case(n, track_file=TRACK_FILE) for n in ("tiny", "mini104", "tiny_flat")}}
     with open(os.path.join(HERE, "reference_digests.json"), "w") as f:
         json.dump(golden, f, indent=1, sort_keys=True)
     print("wrote reference_digests.json:", {k: v["segments_processed"] for k, v in golden["table"].items()})

@@ -214,14 +214,16 @@ class OracleCase(_Base):
             cls._lib = L
         return cls._lib
 
-    def __init__(self, values, seed=1, exp_mode=0, limit_tracks_2D=0):
+    def __init__(self, values, seed=1, exp_mode=0, limit_tracks_2D=0, track_file=None):
         L = self.lib()
-        inp = input_from_values(values)
+        inp = input_from_values(values, track_file)
         L.oracle_derive(C.byref(inp))
         if limit_tracks_2D and limit_tracks_2D < inp.ntracks_2D:
             inp.ntracks_2D = 2 * (limit_tracks_2D // 2)
             inp.ntracks = inp.ntracks_2D * inp.n_polar_angles * inp.z_stacked
         self.h = L.oracle_create(C.byref(inp), seed)
+        if not self.h:
+            raise RuntimeError(f"oracle_create failed (track file {track_file!r})")
         L.oracle_set_exp_mode(self.h, exp_mode)
         self.seed = seed
 
@@ -326,8 +328,9 @@ class OracleCase(_Base):
                 _view(self._ptr("trace_zstart"), (n,)))
 
 
-def input_from_values(values):
-    """An Input as main() would have it after reading an input file (before derive)."""
+def input_from_values(values, track_file=None):
+    """An Input as main() would have it after reading an input file (before derive);
+    track_file: what `-d <file>` adds (src/io.c:160-168)."""
     inp = Input()
     # set_default_input (reference src/init.c:33-74) for what the file does not carry
     inp.mype = 0
@@ -338,6 +341,9 @@ def input_from_values(values):
             inp.decompose = bool(v)
         else:
             setattr(inp, name, v)
+    if track_file:
+        inp.load_tracks = True
+        inp.track_file = os.fsencode(track_file)
     return inp
 
 
@@ -352,6 +358,8 @@ class RefCase(_Base):
             L = C.CDLL(path, mode=C.RTLD_LOCAL)
             L.ref_case_create.restype = C.c_void_p
             L.ref_case_create.argtypes = [C.c_char_p, C.c_int, C.c_uint64, C.c_int, C.c_long]
+            L.ref_case_create_tracks.restype = C.c_void_p
+            L.ref_case_create_tracks.argtypes = [C.c_char_p, C.c_int, C.c_uint64, C.c_int, C.c_long, C.c_char_p]
             L.ref_case_destroy.argtypes = [C.c_void_p]
             L.ref_transport_sweep.restype = C.c_long
             L.ref_transport_sweep.argtypes = [C.c_void_p]
@@ -383,7 +391,7 @@ class RefCase(_Base):
         return cls._libs[variant]
 
     def __init__(self, values=None, seed=1, variant="", small=False, nthreads=1,
-                 limit_tracks_2D=0, tmpdir="/tmp"):
+                 limit_tracks_2D=0, tmpdir="/tmp", track_file=None):
         self.variant = variant
         L = self.lib(variant)
         path = b""
@@ -391,7 +399,8 @@ class RefCase(_Base):
             fn = os.path.join(tmpdir, f"moc_case_{os.getpid()}_{id(self)}.in")
             write_input_file(fn, values)
             path = fn.encode()
-        self.h = L.ref_case_create(path, int(small), seed, nthreads, limit_tracks_2D)
+        self._track_file = os.fsencode(track_file) if track_file else None   # the reference keeps the pointer
+        self.h = L.ref_case_create_tracks(path, int(small), seed, nthreads, limit_tracks_2D, self._track_file)
         if path:
             os.unlink(path.decode())
 

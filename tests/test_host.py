@@ -14,7 +14,8 @@ from oracle_lib import CASES, OracleCase, write_input_file
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 with open(os.path.join(HERE, "golden", "reference_digests.json")) as f:
-    GOLDEN = json.load(f)["table"]
+    _G = json.load(f)
+GOLDEN, GOLDEN_TRACKS = _G["table"], _G["tracks"]
 
 
 def sha(a):
@@ -29,13 +30,16 @@ def test_default_and_small_inputs_derive_the_surveyed_sizes(built):
     assert (s.ntracks_2D, s.z_stacked, s.ntracks, s.n_source_regions_per_node) == (120, 2000, 1200000, 15000)
 
 
-@pytest.mark.parametrize("case", sorted(GOLDEN))
-def test_build_tracks_reproduces_the_reference_draw_for_draw(built, case):
-    """moc_build_tracks == build_tracks (init.c:106-159) of the unmodified reference under the
-    same counter random stream: every array, and the number of draws consumed."""
-    g = GOLDEN[case]
-    host = m.HostProblem(m.derive(m.input_from_values(g["values"])), seed=g["seed"])
+def check_build(g, track_file=None):
+    host = m.HostProblem(m.derive(m.input_from_values(g["values"], track_file)), seed=g["seed"])
     assert host.rand_calls == g["init_rand_calls"]
+    I = host.I
+    derived = {"ntracks_2D": I.ntracks_2D, "z_stacked": I.z_stacked, "ntracks": I.ntracks,
+               "n_source_regions_per_node": I.n_source_regions_per_node}
+    if track_file:
+        derived.update({"n_azimuthal": I.n_azimuthal, "radial_ray_sep": float(I.radial_ray_sep),
+                        "segments_per_track": I.segments_per_track})
+    assert derived == g["derived"]
     got = {"az_weight": sha(host.get(api.HOST_AZ_WEIGHT)), "n_segments": sha(host.get(api.HOST_N_SEGMENTS)),
            "seg_lengths": sha(host.get(api.HOST_SEG_LENGTHS)), "p_weight": sha(host.get(api.ARR_P_WEIGHT)),
            "z_height": sha(host.get(api.ARR_Z_HEIGHT)), "xs": sha(host.get(api.HOST_XS)),
@@ -45,6 +49,68 @@ def test_build_tracks_reproduces_the_reference_draw_for_draw(built, case):
     assert got == g["init"]
     assert not host.get(api.ARR_PSI).any() and not host.get(api.ARR_FINE_FLUX).any()
     host.close()
+
+
+@pytest.mark.parametrize("case", sorted(GOLDEN))
+def test_build_tracks_reproduces_the_reference_draw_for_draw(built, case):
+    """moc_build_tracks == build_tracks (init.c:106-159) of the unmodified reference under the
+    same counter random stream: every array, and the number of draws consumed."""
+    check_build(GOLDEN[case])
+
+
+@pytest.mark.parametrize("case", sorted(GOLDEN_TRACKS))
+def test_build_tracks_from_a_track_file_matches_the_reference(built, case):
+    """`-d <file>`: moc_build_tracks with I->load_tracks == the reference's build_tracks with its own
+    load_OpenMOC_tracks (tracks.c:170-323) on tests/golden/tracks_44.bin: updated Input, every array,
+    the number of draws."""
+    g = GOLDEN_TRACKS[case]
+    check_build(g, os.path.join(HERE, "golden", g["track_file"]))
+
+
+def test_track_file_errors_are_reported_not_undefined(built, tmp_path):
+    """the reference reads whatever fread leaves behind; the library returns MOC_EIO"""
+    from openmoc_tracks import synthetic_tracks, write_track_file
+    vals = CASES["tiny"]
+    with pytest.raises(m.MocError, match="cannot open track file"):
+        m.HostProblem(m.derive(m.input_from_values(vals, str(tmp_path / "missing.bin"))), seed=1)
+    good = write_track_file(str(tmp_path / "good.bin"), [3, 2], synthetic_tracks(1, [3, 2], 6))
+    blob = open(good, "rb").read()
+    for cut in (2, 10, 40, len(blob) // 2, len(blob) - 3):
+        bad = tmp_path / f"cut{cut}.bin"
+        bad.write_bytes(blob[:cut])
+        with pytest.raises(m.MocError, match="track file"):
+            m.HostProblem(m.derive(m.input_from_values(vals, str(bad))), seed=1)
+    # a negative segment count / an absurd azimuthal count
+    import struct
+    hdr = len(struct.pack("=i", 0)) + len(b"test geometry")
+    evil = bytearray(blob)
+    evil[hdr:hdr + 4] = struct.pack("=i", 2 ** 30)
+    (tmp_path / "evil.bin").write_bytes(bytes(evil))
+    with pytest.raises(m.MocError, match="azimuthal"):
+        m.HostProblem(m.derive(m.input_from_values(vals, str(tmp_path / "evil.bin"))), seed=1)
+    # the intact file loads, CMFD flavour included (two more ints per segment, tracks.c:300-304)
+    host = m.HostProblem(m.derive(m.input_from_values(vals, good)), seed=1)
+    assert host.I.ntracks_2D == 5 and host.I.n_azimuthal == 2
+    n_seg = host.get(api.HOST_N_SEGMENTS)
+    lengths = host.get(api.HOST_SEG_LENGTHS)
+    host.close()
+    cm = write_track_file(str(tmp_path / "cmfd.bin"), [3, 2], synthetic_tracks(1, [3, 2], 6), cmfd=True)
+    inp = m.derive(m.input_from_values(vals))
+    t2 = C.c_void_p()
+    total = C.c_long()
+    L = api.lib()
+    L.moc_load_openmoc_tracks.argtypes = [C.c_char_p, C.c_int, C.c_void_p, C.c_uint64, C.c_uint64,
+                                          C.POINTER(C.c_void_p), C.POINTER(C.c_long)]
+    assert L.moc_load_openmoc_tracks(cm.encode(), 1, C.byref(inp), 1, 0, C.byref(t2), C.byref(total)) == 0
+    assert total.value == int(n_seg.sum()) == lengths.size and inp.ntracks_2D == 5
+
+
+def test_cli_dash_d_selects_the_track_file(built):
+    L = api.lib()
+    argv = (C.c_char_p * 4)(b"SimpleMOC", b"-d", b"some/tracks.bin", b"-s")
+    inp = m.default_input()
+    assert L.moc_read_CLI(4, argv, C.byref(inp)) == 0
+    assert inp.load_tracks and inp.track_file == b"some/tracks.bin"       # src/io.c:160-168
 
 
 def test_input_file_and_cli_order(built, tmp_path):
