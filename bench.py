@@ -34,6 +34,7 @@ travel) -- the only place this file touches oracle/.
 """
 import argparse
 import ctypes as C
+import glob
 import json
 import os
 import subprocess
@@ -423,9 +424,22 @@ def run_moc(args):
     hbm_bytes = (2 * 4 * T3 * G + 12 * (state["segments"] / n_launch) + 12 * T3)
     hbm_peak, peak_src = measured_peaks()
     att_per_launch = att_s / n_launch
+    # DRAM bytes of one launch from the committed ncu capture of this workload (profiles/), if there is one
+    traffic, traffic_src = None, None
+    if not (args.egroups or args.decomp_ax or args.limit_tracks_2d) and world == 1:
+        for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_K1_dram_traffic*.json")), reverse=True):
+            try:
+                with open(f) as fh:
+                    t = json.load(fh)
+                if t.get("workload") == args.workload and t.get("exp") == args.exp:
+                    traffic, traffic_src = t["traffic"], os.path.relpath(f, ROOT)
+                    break
+            except (OSError, ValueError, KeyError):
+                pass
     roof = {"kernel": "attenuate_kernel", "bound": "hbm",
             "achieved": hbm_bytes / att_per_launch / 1e9 if att_per_launch > 0 else None,
-            "peak": hbm_peak, "unit": "GB/s", "peak_source": peak_src, "traffic": None,
+            "peak": hbm_peak, "unit": "GB/s", "peak_source": peak_src, "traffic": traffic,
+            "traffic_source": traffic_src, "algorithmic_bytes": hbm_bytes,
             "ms_per_launch": 1e3 * att_per_launch, "share_of_step": state["att_ms"] / ms if ms else None,
             "fp32": {"achieved_tflops": my_integ * FLOP_PER_INTEGRATION / att_s / 1e12 if att_s else None,
                      "peak_tflops_nominal": FP32_PEAK_TFLOPS_NOMINAL,

@@ -209,8 +209,13 @@ enum {
     MOC_OPT_LANES_PER_TRACK = 6,/* override the lane mapping of the attenuation kernel (0=auto)  */
     MOC_OPT_STREAM_CHUNKS = 7,  /* z-stack chunks the host-side transport_sweep moves the angular
                                    flux in (copies overlap kernels), default 16                  */
-    MOC_OPT_WALK_KERNEL = 8     /* axial ray trace: 0 = auto, 1 = one CTA per z-stack, 2 = one
+    MOC_OPT_WALK_KERNEL = 8,    /* axial ray trace: 0 = auto, 1 = one CTA per z-stack, 2 = one
                                    warp per z-stack (needs z_stacked <= 128)                     */
+    MOC_OPT_FILL_OVERLAP = 9,   /* ray-trace CTAs per SM that emit the segment records of batch b+1
+                                   under the attenuation of batch b (0 = emit in front of it);
+                                   warp-per-stack ray trace only.  Default 0: same sweep time on
+                                   a power-capped B200, but 2/batches of the record memory       */
+    MOC_OPT_FILL_BATCHES = 10   /* batches per chunk of z-stacks when the two overlap, default 8 */
 };
 
 /* arrays for moc_get_array / moc_set_array (flat, the reference's slab order) */

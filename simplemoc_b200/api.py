@@ -77,6 +77,7 @@ class SweepTiming(C.Structure):
 OPT_EXP_MODE, OPT_SEED, OPT_RAND_BASE, OPT_BATCH_SEGMENTS, OPT_SOURCE_STRIDE, OPT_LANES = 1, 2, 3, 4, 5, 6
 OPT_STREAM_CHUNKS = 7
 OPT_WALK_KERNEL = 8
+OPT_FILL_OVERLAP, OPT_FILL_BATCHES = 9, 10
 OPT_DIGEST = 100
 OPT_EXACT_RAY_TRACE = 102
 EXP_TABLE_REF, EXP_SFU = 0, 1

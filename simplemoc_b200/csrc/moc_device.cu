@@ -147,6 +147,14 @@ struct moc_handle {
     int iv_fast = 0, fine_fast = 0;   // interval_check_kernel found no mismatch (moc_walk_warp.cuh)
     float iv_lo = 0.f, iv_hi = 0.f;
     int walk_kernel = 0;           // 0 = auto, 1 = one CTA per z-stack, 2 = one warp per z-stack (Z <= 128)
+    // ray-trace CTAs per SM resident under the attenuation of the previous batch.  0 = off, the default:
+    // measured on the default problem the overlapped sweep takes the same time (400 vs 398-408 ms,
+    // profiles/r01_fill_overlap.log) -- the chip runs at its power cap, so hiding one kernel under the
+    // other only slows the other down -- but it needs 2/8 of the record memory (6 GB instead of 25 GB)
+    int fill_overlap_ctas = 0;
+    int fill_batches = 8;          // batches per chunk of z-stacks when the two overlap
+    cudaStream_t fill_stream = nullptr;
+    int n_sm = 0;
     int want_digest = 0;
     // scratch capacity
     long long rec_capacity = 0;
@@ -488,6 +496,7 @@ extern "C" int moc_destroy(moc_handle *h)
     if (h->exch_table) cudaFree(h->exch_table);
     if (h->exch_sums) cudaFree(h->exch_sums);
     if (h->comm_stream) cudaStreamDestroy(h->comm_stream);
+    if (h->fill_stream) cudaStreamDestroy(h->fill_stream);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return MOC_OK;
@@ -680,6 +689,14 @@ extern "C" int moc_set_option(moc_handle *h, int option, long value)
         if (value < 1 || value > 4096) break;
         h->stream_chunks = (int)value;
         return MOC_OK;
+    case MOC_OPT_FILL_OVERLAP:
+        if (value < 0 || value > 8) break;
+        h->fill_overlap_ctas = (int)value;
+        return MOC_OK;
+    case MOC_OPT_FILL_BATCHES:
+        if (value < 2 || value > 1024) break;
+        h->fill_batches = (int)value;
+        return MOC_OK;
     case 100: h->want_digest = value != 0; return MOC_OK;   // MOC_OPT_DIGEST (diagnostic)
     case 102:                                                // diagnostic: 1 = ray trace with IEEE divisions / hardware remainders only
         if (value) h->iv_fast = h->fine_fast = h->mod_fast = 0;
@@ -704,6 +721,8 @@ extern "C" long moc_get_option(moc_handle *h, int option)
     case MOC_OPT_LANES_PER_TRACK: return h->lanes_override;
     case MOC_OPT_STREAM_CHUNKS: return h->stream_chunks;
     case MOC_OPT_WALK_KERNEL: return h->walk_kernel;
+    case MOC_OPT_FILL_OVERLAP: return h->fill_overlap_ctas;
+    case MOC_OPT_FILL_BATCHES: return h->fill_batches;
     case 100: return h->want_digest;
     case 101: return !h->fast_cell_ok;
     case 102: return !(h->iv_fast && h->fine_fast && h->mod_fast);
@@ -766,9 +785,11 @@ static WalkParams walk_params(const moc_handle *h)
 }
 
 template <bool FILL>
-static void launch_walk(const moc_handle *h, const WalkParams &w, long long n_pairs)
+static void launch_walk(const moc_handle *h, const WalkParams &w, long long n_pairs, cudaStream_t st = nullptr,
+                        unsigned max_ctas = 0)
 {
     if (n_pairs <= 0) return;
+    if (!st) st = h->stream;
     const int Z = h->Z;
     if (h->walk_kernel != 1 && Z <= 128) {
         // short stacks: one warp per stack, 4 stacks per CTA, one launch per ray direction
@@ -780,9 +801,10 @@ static void launch_walk(const moc_handle *h, const WalkParams &w, long long n_pa
         const bool fast = h->iv_fast && h->fine_fast;
 #define MOC_WALK(K, UP, before, n)                                                                                \
     if (kpt == K && (n) > 0) {                                                                                    \
-        const unsigned grid = (unsigned)(((n) + 3) / 4);                                                          \
-        if (fast) stack_walk_warp_kernel<K, FILL, UP, true><<<grid, 128, 0, h->stream>>>(w, before, n);           \
-        else stack_walk_warp_kernel<K, FILL, UP, false><<<grid, 128, 0, h->stream>>>(w, before, n);               \
+        unsigned grid = (unsigned)(((n) + 3) / 4);                                                                \
+        if (max_ctas && grid > max_ctas) grid = max_ctas; /* resident grid: warps stride over the stacks */       \
+        if (fast) stack_walk_warp_kernel<K, FILL, UP, true><<<grid, 128, 0, st>>>(w, before, n);                  \
+        else stack_walk_warp_kernel<K, FILL, UP, false><<<grid, 128, 0, st>>>(w, before, n);                      \
         h->launch_count++;                                                                                        \
     }
         MOC_WALK(1, true, up0, n_up) MOC_WALK(2, true, up0, n_up) MOC_WALK(3, true, up0, n_up) MOC_WALK(4, true, up0, n_up)
@@ -798,11 +820,11 @@ static void launch_walk(const moc_handle *h, const WalkParams &w, long long n_pa
     const unsigned grid = (unsigned)n_pairs;
     h->launch_count++;
     switch (kpt) {
-    case 1: stack_walk_kernel<1, FILL><<<grid, threads, 0, h->stream>>>(w); break;
-    case 2: stack_walk_kernel<2, FILL><<<grid, threads, 0, h->stream>>>(w); break;
-    case 4: stack_walk_kernel<4, FILL><<<grid, threads, 0, h->stream>>>(w); break;
-    case 8: stack_walk_kernel<8, FILL><<<grid, threads, 0, h->stream>>>(w); break;
-    default: stack_walk_kernel<16, FILL><<<grid, threads, 0, h->stream>>>(w); break;
+    case 1: stack_walk_kernel<1, FILL><<<grid, threads, 0, st>>>(w); break;
+    case 2: stack_walk_kernel<2, FILL><<<grid, threads, 0, st>>>(w); break;
+    case 4: stack_walk_kernel<4, FILL><<<grid, threads, 0, st>>>(w); break;
+    case 8: stack_walk_kernel<8, FILL><<<grid, threads, 0, st>>>(w); break;
+    default: stack_walk_kernel<16, FILL><<<grid, threads, 0, st>>>(w); break;
     }
 }
 
@@ -1048,21 +1070,31 @@ static int sweep_core(moc_handle *h, long *segments_processed, const HostLayout 
         moc_set_error("a single z-stack needs %llu record slots (> 2^32)", largest_pair);
         return MOC_EINVAL;
     }
+    // The emitting pass of the ray trace is issue-bound on the ALU/XU pipes, the attenuation on the FMA
+    // pipe and the L2: with the warp-per-stack ray trace the records of batch b+1 are emitted by a few
+    // resident CTAs per SM UNDER the attenuation of batch b (second stream, two record buffers) instead
+    // of by a full grid in front of it.
+    const bool overlap_fill = h->fill_overlap_ctas > 0 && h->walk_kernel != 1 && h->Z <= 128;
+    const unsigned long long nbuf = overlap_fill ? 2 : 1;
     // 10 % headroom: the record rows a stack needs (its longest ray) drift from sweep to sweep (stale
     // ray heights, solver.c:514-523) and re-allocating multi-GB staging buffers costs ~0.2 s
-    const unsigned long long want = largest_chunk + largest_chunk / 10 + 1024;
-    long long cap = h->batch_segments;
-    if (cap <= 0 && (long long)largest_chunk <= h->rec_capacity) {
-        cap = h->rec_capacity;   // the staging buffers of the previous sweep are large enough
+    unsigned long long target = largest_chunk;
+    if (overlap_fill) target = std::max(largest_pair, (largest_chunk + h->fill_batches - 1) / (unsigned long long)h->fill_batches);
+    const unsigned long long want = target + target / 10 + 1024;
+    long long cap = h->batch_segments;   // records per batch
+    if (cap <= 0 && target * nbuf <= (unsigned long long)h->rec_capacity) {
+        // the staging buffers of the previous sweep are large enough
+        cap = (long long)std::min<unsigned long long>((unsigned long long)h->rec_capacity / nbuf, overlap_fill ? want : ~0ull);
     } else if (cap <= 0) {
         size_t free_b = 0, total_b = 0;
         CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
         free_b += (size_t)h->rec_capacity * 12;   // what we already hold can be reused
-        cap = (long long)((double)free_b * 0.7 / 12.0);
+        cap = (long long)((double)free_b * 0.7 / 12.0 / (double)nbuf);
     }
     if ((unsigned long long)cap < largest_pair) cap = (long long)largest_pair;
     if (cap >= (1ll << 32)) cap = (1ll << 32) - 1;
-    long long need = (long long)std::min<unsigned long long>(want, (unsigned long long)cap);
+    const long long slot = (long long)std::min<unsigned long long>(std::max(want, largest_pair), (unsigned long long)cap);
+    long long need = slot * (long long)nbuf;
     struct Batch {
         long long first, end;
         size_t chunk;
@@ -1073,7 +1105,7 @@ static int sweep_core(moc_handle *h, long *segments_processed, const HostLayout 
         long long p = chunk_first[c];
         const long long pe = chunk_first[c + 1];
         while (p < pe) {
-            const unsigned long long lim = base[p] + (unsigned long long)cap;
+            const unsigned long long lim = base[p] + (unsigned long long)slot;
             // largest q with base[q] <= lim
             long long q = (long long)(std::upper_bound(base + p, base + pe + 1, lim) - base) - 1;
             if (q <= p) q = p + 1;
@@ -1121,10 +1153,31 @@ static int sweep_core(moc_handle *h, long *segments_processed, const HostLayout 
         h->launch_count++;
     }
 
-    // three events per batch: before the fill, between fill and attenuation, after
+    // three events per batch: before the fill, after it (on the stream that ran it), after the attenuation
     std::vector<cudaEvent_t> ev_b(3 * batches.size());
     for (auto &e : ev_b)
         if ((rc = event_at(h, ev_next++, &e))) return rc;
+    const bool two_streams = overlap_fill && batches.size() > 1;
+    if (two_streams && !h->fill_stream) {
+        // highest priority: the few ray-trace CTAs become resident as soon as attenuation CTAs retire
+        int least = 0, greatest = 0;
+        CUDA_TRY(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        CUDA_TRY(cudaStreamCreateWithPriority(&h->fill_stream, cudaStreamNonBlocking, greatest));
+    }
+    if (two_streams && !h->n_sm) CUDA_TRY(cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, h->device));
+    // batch bi lives in record buffer bi & 1 (one buffer without the overlap)
+    auto emit = [&](size_t bi, cudaStream_t st, unsigned max_ctas) {
+        const Batch &b = batches[bi];
+        const size_t off = two_streams ? (bi & 1) * (size_t)slot : 0;
+        w.first_pair = b.first;
+        w.batch_first_record = base[b.first];
+        w.rec_ds = h->d.rec_ds + off;
+        w.rec_zin = h->d.rec_zin + off;
+        w.rec_code = h->d.rec_code + off;
+        cudaEventRecord(ev_b[3 * bi], st);
+        launch_walk<true>(h, w, b.end - b.first, st, max_ctas);
+        cudaEventRecord(ev_b[3 * bi + 1], st);
+    };
     size_t chunk_start_batch = 0;
     for (size_t bi = 0; bi < batches.size(); bi++) {
         const Batch &b = batches[bi];
@@ -1132,12 +1185,22 @@ static int sweep_core(moc_handle *h, long *segments_processed, const HostLayout 
             CUDA_TRY(cudaStreamWaitEvent(h->stream, ev_up[b.chunk], 0));   // this chunk's flux has arrived
             chunk_start_batch = bi;
         }
-        w.first_pair = b.first;
-        w.batch_first_record = base[b.first];
+        if (!two_streams || bi == 0) emit(bi, h->stream, 0);   // nothing to hide behind: full grid, in front
+        if (two_streams) {
+            if (bi + 1 < batches.size()) {
+                // records of the next batch, under this batch's attenuation; its buffer was last read by
+                // the attenuation of batch bi - 1
+                if (bi >= 1) CUDA_TRY(cudaStreamWaitEvent(h->fill_stream, ev_b[3 * (bi - 1) + 2], 0));
+                else CUDA_TRY(cudaStreamWaitEvent(h->fill_stream, e_scan, 0));
+                emit(bi + 1, h->fill_stream, (unsigned)(h->n_sm * h->fill_overlap_ctas));
+            }
+            if (bi >= 1) CUDA_TRY(cudaStreamWaitEvent(h->stream, ev_b[3 * bi + 1], 0));
+        }
+        const size_t off = two_streams ? (bi & 1) * (size_t)slot : 0;
+        a.rec_ds = h->d.rec_ds + off;
+        a.rec_zin = h->d.rec_zin + off;
+        a.rec_code = h->d.rec_code + off;
         a.batch_first_record = base[b.first];
-        CUDA_TRY(cudaEventRecord(ev_b[3 * bi], h->stream));
-        launch_walk<true>(h, w, b.end - b.first);
-        CUDA_TRY(cudaEventRecord(ev_b[3 * bi + 1], h->stream));
         a.first_track = b.first * h->Z;
         a.end_track = b.end * h->Z;
         if ((rc = launch_attenuate(h, a, a.end_track - a.first_track))) return rc;
@@ -1194,11 +1257,17 @@ static int sweep_core(moc_handle *h, long *segments_processed, const HostLayout 
     CUDA_TRY(cudaEventRecord(e_end, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     CUDA_TRY(cudaGetLastError());
+    // with the overlap the two phases run concurrently: fill_ms is the time the emitting kernels were
+    // resident, attenuate_ms the time from "records ready and previous batch done" to the batch's end
     float fill_ms = 0.f, att_ms = 0.f;
     for (size_t bi = 0; bi < batches.size(); bi++) {
-        float f = 0, t = 0;
+        float f = 0, t = 0, t2 = 0;
         cudaEventElapsedTime(&f, ev_b[3 * bi], ev_b[3 * bi + 1]);
         cudaEventElapsedTime(&t, ev_b[3 * bi + 1], ev_b[3 * bi + 2]);
+        if (two_streams && bi >= 1) {
+            cudaEventElapsedTime(&t2, ev_b[3 * (bi - 1) + 2], ev_b[3 * bi + 2]);
+            t = std::min(t, t2);
+        }
         fill_ms += f;
         att_ms += t;
     }

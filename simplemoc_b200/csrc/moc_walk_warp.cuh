@@ -422,16 +422,20 @@ __device__ __forceinline__ void walk_stack_warp(const WalkParams &w, const long 
 // rest), so only one instantiation of the walk is resident in the instruction caches at a time.
 // n_dir = number of stacks of that direction among pairs [first_pair, first_pair + n_pairs);
 // dir_before = number of them among pairs [0, first_pair).  4 warps (stacks) per CTA.
+// The grid may be smaller than the work (warps stride over the stacks): the emitting pass of batch b+1
+// runs as a few resident CTAs per SM UNDER the attenuation of batch b (sweep_core), filling the issue
+// slots that kernel leaves idle, instead of as a full grid in front of it.
 template <int KPT, bool FILL, bool UP, bool FAST>
 __global__ void __launch_bounds__(128) stack_walk_warp_kernel(const WalkParams w, long long dir_before, long long n_dir)
 {
     const int lane = threadIdx.x & 31;
-    const long long q = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (q >= n_dir) return;   // whole warps leave together
     const int H = w.P / 2, per_track = UP ? H : w.P - H;
-    const long long target = dir_before + q;
-    const long long i = target / per_track;
-    const int j = (int)(target - i * per_track) + (UP ? 0 : H);
-    const long long pair = i * w.P + j;
-    walk_stack_warp<KPT, FILL, UP, FAST>(w, pair, pair - w.first_pair, i, j, lane);
+    const long long step = (long long)gridDim.x * (blockDim.x >> 5);
+    for (long long q = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); q < n_dir; q += step) {
+        const long long target = dir_before + q;   // whole warps stay or leave together
+        const long long i = target / per_track;
+        const int j = (int)(target - i * per_track) + (UP ? 0 : H);
+        const long long pair = i * w.P + j;
+        walk_stack_warp<KPT, FILL, UP, FAST>(w, pair, pair - w.first_pair, i, j, lane);
+    }
 }

@@ -124,6 +124,24 @@ def test_batching_is_invisible(built, batch):
     dev.close(); host.close(); oracle.close()
 
 
+@pytest.mark.parametrize("case,ctas,batches", [("tiny", 1, 8), ("mini104", 2, 5), ("mini_default_in", 1, 3)])
+def test_emitting_pass_under_the_attenuation_is_invisible(built, case, ctas, batches):
+    """MOC_OPT_FILL_OVERLAP: the segment records of batch b+1 are emitted by a few resident CTAs per SM on
+    a second stream while batch b is attenuated (two record buffers).  Same integers, same flux."""
+    host, dev, oracle = make_pair(case, seed=4)
+    dev.set_option(api.OPT_FILL_OVERLAP, ctas)
+    dev.set_option(api.OPT_FILL_BATCHES, batches)
+    for sweep in range(2):
+        assert dev.sweep() == oracle.sweep()
+        assert dev.timing().n_batches >= 2
+        assert np.array_equal(dev.get(api.ARR_SEG_COUNT), oracle.seg_count)
+        assert np.array_equal(dev.get(api.ARR_QSR_DIGEST), oracle.digest)
+        assert np.array_equal(dev.get(api.ARR_Z_HEIGHT), oracle.z_height)
+        if sweep == 0:
+            check_state(dev, oracle, f"{case} overlapped emit", noise_cap=256)
+    dev.close(); host.close(); oracle.close()
+
+
 @pytest.mark.parametrize("case,walk,exact", [("short", 0, False), ("short", 1, False), ("tiny", 1, False),
                                              ("odd", 1, False), ("mini104", 1, False), ("mini104", 2, False),
                                              ("tall", 0, False), ("tiny_flat", 1, False), ("tiny", 2, True),
