@@ -176,10 +176,19 @@ __device__ __forceinline__ float rcp_groups(float s) { return rcp_approx(s); }
 //   out = q0 E / sigT + q1 mu (tau - E) / sigT^2 + q2 mu^2 R + psi (1 - E)
 //   R   = tau (tau - 2) + 2 E / sigT^3          (solver.c:175-176 as parenthesised there)
 //   C3  = [tau (tau (tau - 3) + 6) - 6 E] / 3
-template <int MODE, typename V>
+// COEF = false (source slabs larger than the L2, where three more rows per region would only add DRAM
+// traffic): (c0, d, e) arrive as the three source rows (y1, y2, y3) of the stencil and the fit is done here,
+// with the scalars a1 = zin/(2dz), a2 = zin^2/(2dz^2), b1 = mu/(2dz), b2 = 2 mu zin/(2dz^2), b3 = mu^2/(2dz^2).
+template <int MODE, bool COEF, typename V>
 __device__ __forceinline__ V attenuate_groups(V c0, V d, V e, V sigT, V &psi, const SegmentScalars &k,
                                               const TableConsts &tc)
 {
+    if (!COEF) {
+        const V y1 = c0, y2 = d, y3 = e;
+        c0 = y2;
+        d = sub2(y1, y3);
+        e = fma2(splat<V>(-2.f), y2, add2(y1, y3));
+    }
     const V q0 = fma2(splat<V>(k.a2), e, fma2(splat<V>(k.a1), d, c0));
     const V q1m = fma2(splat<V>(k.b2), e, mul2(splat<V>(k.b1), d));   // q1 * mu
     const V q2m = mul2(splat<V>(k.b3), e);                            // q2 * mu^2
@@ -260,7 +269,7 @@ __device__ __forceinline__ void red_add(float *addr, float v)
 // g = 4*L*NV4 + lit + L*s  (so G=104 -> L=8, NV4=3, NS=1 uses every lane fully).
 // The angular flux of the track lives in registers for the whole track.
 // GC: the number of groups as a compile-time constant (row strides become immediates), 0 = a.G.
-template <int L, int NV4, int NS, int MODE, bool FLAT, int GC>
+template <int L, int NV4, int NS, int MODE, bool FLAT, int GC, bool COEF>
 __global__ void __launch_bounds__(128, MOC_ATT_MIN_BLOCKS) attenuate_kernel(const AttenuateParams a)
 {
     extern __shared__ float s_tab[];   // [n+1] x (slope, intercept)
@@ -298,10 +307,10 @@ __global__ void __launch_bounds__(128, MOC_ATT_MIN_BLOCKS) attenuate_kernel(cons
         float w0 = __fmul_rn(a.p_weight[t], a.az_weight[i]);   // solver.c:49
         if (FLAT) w0 = __fmul_rn(w0, mu);                      // solver.c:1064
         sc.weight = w0;
-        sc.b1 = mu;
-        sc.b3 = mu * mu;
+        sc.b1 = COEF ? mu : mu * a.inv_2dz;
+        sc.b3 = COEF ? mu * mu : mu * mu * a.inv_2dz2;
     }
-    const float two_mu = 2.f * mu;
+    const float two_mu = COEF ? 2.f * mu : 2.f * mu * a.inv_2dz2;
     unsigned int longest = n_rec;
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {
@@ -340,7 +349,7 @@ __global__ void __launch_bounds__(128, MOC_ATT_MIN_BLOCKS) attenuate_kernel(cons
         nxt_zin = __ldg(rec_zin + lit * Zs);
         nxt_code = __ldg(rec_code + lit * Zs);
     }
-    const float *const src_base = FLAT ? a.fine_source : a.coef;   // quadratic source: fit coefficients
+    const float *const src_base = COEF ? a.coef : a.fine_source;   // fit coefficients, or the source rows themselves
     const float *const src_q = src_base + 4 * lit;               // this lane's quads
     const float *const sig_q = a.sigT + 4 * lit;
     float *const flx_q = a.fine_flux + 4 * lit;
@@ -364,17 +373,17 @@ __global__ void __launch_bounds__(128, MOC_ATT_MIN_BLOCKS) attenuate_kernel(cons
         const uint32_t code = __shfl_sync(0xffffffffu, cur_code, slot, L);
         if (sgm < n_rec) {
             sc.ds = seg_ds;
-            sc.a1 = zin;
-            sc.a2 = zin * zin;
+            sc.a1 = COEF ? zin : zin * a.inv_2dz;
+            sc.a2 = COEF ? zin * zin : zin * zin * a.inv_2dz2;
             sc.b2 = two_mu * zin;
             const uint32_t qsr = code & 0xffffffu;
             const uint32_t r0 = (code >> 24) & 63u;
             const uint32_t which = code >> 30;
             // element offsets inside the source slab (< 2^32, checked by moc_create)
-            // quadratic source: o_src addresses the (c0, c1, c2) rows of stencil r0 in the coefficient slab;
-            // flat source: the source row itself (r0 = fine interval)
+            // COEF: o_src addresses the (c0, c1, c2) rows of stencil r0 in the coefficient slab; otherwise the
+            // first source row of the stencil (flat source: r0 = the fine interval itself)
             const uint32_t o_row = (qsr * a.fai + r0) * (uint32_t)W;
-            const uint32_t o_src = FLAT ? o_row : (qsr * a.coef_stencils + r0) * 3u * (uint32_t)W;
+            const uint32_t o_src = COEF ? (qsr * a.coef_stencils + r0) * 3u * (uint32_t)W : o_row;
             const uint32_t o_sig = qsr * (uint32_t)W;
             const uint32_t o_flx = o_row + which * (uint32_t)W;
 #pragma unroll
@@ -394,10 +403,10 @@ __global__ void __launch_bounds__(128, MOC_ATT_MIN_BLOCKS) attenuate_kernel(cons
                         const float4 k1 = __ldg(reinterpret_cast<const float4 *>(src_q + o_src + W + 4 * L * v));
                         const float4 k2 = __ldg(reinterpret_cast<const float4 *>(src_q + o_src + 2 * W + 4 * L * v));
                         float2 plo = make_float2(psi4[v].x, psi4[v].y), phi = make_float2(psi4[v].z, psi4[v].w);
-                        const float2 tlo = attenuate_groups<MODE>(
+                        const float2 tlo = attenuate_groups<MODE, COEF>(
                             make_float2(k0.x, k0.y), make_float2(k1.x, k1.y), make_float2(k2.x, k2.y),
                             make_float2(s4.x, s4.y), plo, sc, tc);
-                        const float2 thi = attenuate_groups<MODE>(
+                        const float2 thi = attenuate_groups<MODE, COEF>(
                             make_float2(k0.z, k0.w), make_float2(k1.z, k1.w), make_float2(k2.z, k2.w),
                             make_float2(s4.z, s4.w), phi, sc, tc);
                         psi4[v] = make_float4(plo.x, plo.y, phi.x, phi.y);
@@ -416,7 +425,7 @@ __global__ void __launch_bounds__(128, MOC_ATT_MIN_BLOCKS) attenuate_kernel(cons
                         tally = attenuate_flat<MODE>(__ldg(src_s + o_src + L * s), s1, psi1[s], sc, tc);
                     } else {
                         // the tail group runs on scalar FFMA/FMUL/FADD, not on a half-empty pair
-                        tally = attenuate_groups<MODE>(__ldg(src_s + o_src + L * s), __ldg(src_s + o_src + W + L * s),
+                        tally = attenuate_groups<MODE, COEF>(__ldg(src_s + o_src + L * s), __ldg(src_s + o_src + W + L * s),
                                                        __ldg(src_s + o_src + 2 * W + L * s), s1, psi1[s], sc, tc);
                     }
                     red_add(flx_s + o_flx + L * s, tally);

@@ -153,6 +153,7 @@ struct moc_handle {
     // other only slows the other down -- but it needs 2/8 of the record memory (6 GB instead of 25 GB)
     int fill_overlap_ctas = 0;
     int fill_batches = 8;          // batches per chunk of z-stacks when the two overlap
+    int fit_per_segment = 0;       // diagnostic: 1 = never use the coefficient slab
     cudaStream_t fill_stream = nullptr;
     int n_sm = 0;
     int want_digest = 0;
@@ -572,7 +573,17 @@ static int create_common(const Input *I, const Params *P, int device, int source
     if ((rc = dev_alloc(&h->d.psi, 2 * T3 * G))) return fail(rc);
     if ((rc = dev_alloc(&h->d.src, (2 * F + 1) * N * (size_t)h->Gp))) return fail(rc);
     cudaMemsetAsync(h->d.src, 0, sizeof(float) * (2 * F + 1) * N * (size_t)h->Gp, h->stream);   // padding columns stay 0
-    if (I->axial_exp == 2 && (rc = dev_alloc(&h->d.coef, 3 * (size_t)(F - 2) * N * (size_t)h->Gp))) return fail(rc);
+    {
+        // K1 gathers per-stencil fit coefficients if what it then gathers from -- coefficients, sigT, scalar
+        // flux -- still fits the L2; on larger problems (SURVEY config 5: 518 MB against 380 MB) every gather
+        // goes to DRAM anyway and three more rows per region only add traffic, so the fit stays per segment
+        int l2_bytes = 0;
+        cudaDeviceGetAttribute(&l2_bytes, cudaDevAttrL2CacheSize, device);
+        const double coef_set = (3.0 * (F - 2) + F + 1) * (double)N * h->Gp * sizeof(float);
+        if (I->axial_exp == 2 && coef_set <= (double)l2_bytes &&
+            (rc = dev_alloc(&h->d.coef, 3 * (size_t)(F - 2) * N * (size_t)h->Gp)))
+            return fail(rc);
+    }
     if ((rc = dev_alloc(&h->d.seg_count, T3))) return fail(rc);
     if ((rc = dev_alloc(&h->d.pair_count, pairs))) return fail(rc);
     if ((rc = dev_alloc(&h->d.pair_base, pairs + 1))) return fail(rc);
@@ -697,6 +708,7 @@ extern "C" int moc_set_option(moc_handle *h, int option, long value)
         if (value < 2 || value > 1024) break;
         h->fill_batches = (int)value;
         return MOC_OK;
+    case 103: h->fit_per_segment = value != 0; return MOC_OK;   // diagnostic: quadratic fit per segment (large-slab path)
     case 100: h->want_digest = value != 0; return MOC_OK;   // MOC_OPT_DIGEST (diagnostic)
     case 102:                                                // diagnostic: 1 = ray trace with IEEE divisions / hardware remainders only
         if (value) h->iv_fast = h->fine_fast = h->mod_fast = 0;
@@ -723,6 +735,7 @@ extern "C" long moc_get_option(moc_handle *h, int option)
     case MOC_OPT_WALK_KERNEL: return h->walk_kernel;
     case MOC_OPT_FILL_OVERLAP: return h->fill_overlap_ctas;
     case MOC_OPT_FILL_BATCHES: return h->fill_batches;
+    case 103: return h->fit_per_segment || !h->d.coef;
     case 100: return h->want_digest;
     case 101: return !h->fast_cell_ok;
     case 102: return !(h->iv_fast && h->fine_fast && h->mod_fast);
@@ -863,15 +876,19 @@ static int launch_attenuate_mode(const moc_handle *h, const AttenuateParams &a, 
     // 0: table, IEEE division; 1: table, verified fast division; 2: SFU
     const int mode = h->exp_mode == 1 ? 2 : (h->fast_cell_ok ? 1 : 0);
     h->launch_count++;
-#define MOC_LAUNCH(M, F) attenuate_kernel<L, NV4, NS, M, F, GC><<<grid, 128, (M) == 2 ? 0 : smem, h->stream>>>(a)
-    if (!flat) {
-        if (mode == 0) MOC_LAUNCH(0, false);
-        else if (mode == 1) MOC_LAUNCH(1, false);
-        else MOC_LAUNCH(2, false);
+#define MOC_LAUNCH(M, F, C) attenuate_kernel<L, NV4, NS, M, F, GC, C><<<grid, 128, (M) == 2 ? 0 : smem, h->stream>>>(a)
+    if (!flat && a.coef) {
+        if (mode == 0) MOC_LAUNCH(0, false, true);
+        else if (mode == 1) MOC_LAUNCH(1, false, true);
+        else MOC_LAUNCH(2, false, true);
+    } else if (!flat) {
+        if (mode == 0) MOC_LAUNCH(0, false, false);
+        else if (mode == 1) MOC_LAUNCH(1, false, false);
+        else MOC_LAUNCH(2, false, false);
     } else {
-        if (mode == 0) MOC_LAUNCH(0, true);
-        else if (mode == 1) MOC_LAUNCH(1, true);
-        else MOC_LAUNCH(2, true);
+        if (mode == 0) MOC_LAUNCH(0, true, false);
+        else if (mode == 1) MOC_LAUNCH(1, true, false);
+        else MOC_LAUNCH(2, true, false);
     }
 #undef MOC_LAUNCH
     return MOC_OK;
@@ -1129,8 +1146,10 @@ static int sweep_core(moc_handle *h, long *segments_processed, const HostLayout 
     a.mu = h->d.mu;
     a.psi = h->d.psi;
     a.fine_source = h->d.src;
-    a.coef = h->d.coef;
+    a.coef = h->fit_per_segment ? nullptr : h->d.coef;
     a.coef_stencils = h->F - 2;
+    a.inv_2dz = 1.0f / (2.f * w.dz_fine);
+    a.inv_2dz2 = 1.0f / (2.f * w.dz_fine * w.dz_fine);
     a.fine_flux = h->d.src + (size_t)h->N * h->F * h->Gp;
     a.sigT = h->d.src + (size_t)2 * h->N * h->F * h->Gp;
     a.pitch = h->Gp;
@@ -1145,7 +1164,7 @@ static int sweep_core(moc_handle *h, long *segments_processed, const HostLayout 
     a.G = h->G;
     a.fai = h->F;
 
-    if (h->d.coef) {
+    if (a.coef) {
         // the source only changes between sweeps (update_sources, uploads): fit every stencil once
         const long long cells = h->N * (h->F - 2) * (long long)h->Gp;
         fit_coefficients_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, h->stream>>>(

@@ -99,6 +99,7 @@ struct AttenuateParams {
     int table_n;
     long long first_track, end_track; // tracks of this batch
     int P, Z, G, fai;
+    float inv_2dz, inv_2dz2;          // 1/(2 dz), 1/(2 dz dz) of solver.c:75-76 (only when the fit is done per segment)
 };
 
 // record code: | which:2 | r0:6 | qsr:24 |   (stencil rows r0..r0+2, tally row r0+which)

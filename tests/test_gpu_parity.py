@@ -124,6 +124,19 @@ def test_batching_is_invisible(built, batch):
     dev.close(); host.close(); oracle.close()
 
 
+@pytest.mark.parametrize("case", ["mini104", "odd", "onecell"])
+def test_fit_per_segment_path(built, case):
+    """Source slabs larger than the L2 (SURVEY config 5) keep the quadratic fit of solver.c:74-76 inside the
+    attenuation kernel instead of gathering per-stencil coefficients; forced here on small cases."""
+    host, dev, oracle = make_pair(case, seed=6)
+    dev.set_option(api.OPT_FIT_PER_SEGMENT, 1)
+    assert dev.get_option(api.OPT_FIT_PER_SEGMENT) == 1
+    assert dev.sweep() == oracle.sweep()
+    assert np.array_equal(dev.get(api.ARR_QSR_DIGEST), oracle.digest)
+    check_state(dev, oracle, f"{case} fit per segment", noise_cap=256)
+    dev.close(); host.close(); oracle.close()
+
+
 @pytest.mark.parametrize("case,ctas,batches", [("tiny", 1, 8), ("mini104", 2, 5), ("mini_default_in", 1, 3)])
 def test_emitting_pass_under_the_attenuation_is_invisible(built, case, ctas, batches):
     """MOC_OPT_FILL_OVERLAP: the segment records of batch b+1 are emitted by a few resident CTAs per SM on
