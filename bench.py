@@ -296,7 +296,7 @@ def run_reference(args):
             "ns_per_integration": 1e9 / value, "cpu_baseline": desc,
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(finite(line), allow_nan=False), flush=True)
+    emit_line(json.dumps(finite(line), allow_nan=False))
 
 
 # ------------------------------------------------------------------ the CUDA path
@@ -490,7 +490,7 @@ def run_moc(args):
                 "cpu_baseline": cpu}
         if args.limit_tracks_2d:
             line["config"]["limit_tracks_2d"] = args.limit_tracks_2d
-        print(json.dumps(finite(line), allow_nan=False), flush=True)
+        emit_line(json.dumps(finite(line), allow_nan=False))
     dev.close()
     if host is not None:
         host.close()
@@ -544,8 +544,27 @@ def measure_e2e(args, m, api, host, dev, torch, dist, world, rank, local):
                     "the library's stream around upload + sweep + download"}
 
 
+_RESULT_FD = None
+
+
+def claim_stdout():
+    """stdout carries exactly ONE line, the JSON result.  Native libraries write there too (NCCL prints
+    "NCCL version ..." to stdout when NCCL_DEBUG is set in the environment): keep a private duplicate of the
+    real stdout for the result and point fd 1 at stderr for everybody else."""
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit_line(text):
+    sys.stdout.flush()
+    os.write(_RESULT_FD if _RESULT_FD is not None else 1, (text + "\n").encode())
+
+
 def main():
     args = parse_args()
+    claim_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
