@@ -148,6 +148,16 @@ long ref_transport_sweep(RefCase *c)
     return c->I.segments_processed;
 }
 
+/* solver.c:556-891: compiled into the reference but not declared in its header (never called by main.c) */
+void two_way_transport_sweep(Params *params, Input *I);
+long ref_two_way_transport_sweep(RefCase *c)
+{
+    int saved = quiet_begin();
+    two_way_transport_sweep(&c->P, &c->I);
+    quiet_end(saved);
+    return c->I.segments_processed;
+}
+
 double ref_time_transport_sweep(RefCase *c)
 {
     struct timespec t0, t1;

@@ -185,6 +185,8 @@ class OracleCase(_Base):
             L.oracle_derive.argtypes = [C.POINTER(Input)]
             L.oracle_sweep.restype = C.c_long
             L.oracle_sweep.argtypes = [C.c_void_p]
+            L.oracle_two_way_sweep.restype = C.c_long
+            L.oracle_two_way_sweep.argtypes = [C.c_void_p]
             L.oracle_renormalize.argtypes = [C.c_void_p]
             L.oracle_update_sources.restype = C.c_float
             L.oracle_update_sources.argtypes = [C.c_void_p, C.c_float]
@@ -196,12 +198,12 @@ class OracleCase(_Base):
             for n in ("rand_calls", "init_rand_calls"):
                 getattr(L, "oracle_" + n).restype = C.c_uint64
                 getattr(L, "oracle_" + n).argtypes = [C.c_void_p]
-            for n in ("n_xs_regions", "total_2d_segments", "trace_len"):
+            for n in ("n_xs_regions", "total_2d_segments", "trace_len", "table_oob"):
                 getattr(L, "oracle_" + n).restype = C.c_long
                 getattr(L, "oracle_" + n).argtypes = [C.c_void_p]
             for n in ("psi", "source_data", "xs_data", "scatter_data", "polar_angles",
                       "p_weight", "z_height", "az_weight", "n_segments", "seg_lengths",
-                      "xs_index", "vol", "table_values", "leakage", "seg_count", "digest", "abs_flux",
+                      "xs_index", "vol", "table_values", "leakage", "seg_count", "digest", "digest_back", "abs_flux",
                       "trace_track", "trace_row", "trace_ds", "trace_zstart"):
                 getattr(L, "oracle_" + n).restype = C.c_void_p
                 getattr(L, "oracle_" + n).argtypes = [C.c_void_p]
@@ -308,6 +310,19 @@ class OracleCase(_Base):
     def sweep(self):
         return self.lib().oracle_sweep(self.h)
 
+    def two_way_sweep(self):
+        """solver.c:556-891 (the v1 sweep, forward + backward flux)"""
+        return self.lib().oracle_two_way_sweep(self.h)
+
+    @property
+    def table_oob(self):
+        """two-way sweep: table lookups below cell 0 (out-of-bounds reads in the reference)"""
+        return self.lib().oracle_table_oob(self.h)
+
+    @property
+    def digest_back(self):
+        return _view(self._ptr("digest_back"), (4,), np.uint64)
+
     def renormalize(self):
         self.lib().oracle_renormalize(self.h)
 
@@ -363,6 +378,8 @@ class RefCase(_Base):
             L.ref_case_destroy.argtypes = [C.c_void_p]
             L.ref_transport_sweep.restype = C.c_long
             L.ref_transport_sweep.argtypes = [C.c_void_p]
+            L.ref_two_way_transport_sweep.restype = C.c_long
+            L.ref_two_way_transport_sweep.argtypes = [C.c_void_p]
             L.ref_time_transport_sweep.restype = C.c_double
             L.ref_time_transport_sweep.argtypes = [C.c_void_p]
             L.ref_renormalize_flux.argtypes = [C.c_void_p]
@@ -468,6 +485,10 @@ class RefCase(_Base):
 
     def sweep(self):
         return self.lib(self.variant).ref_transport_sweep(self.h)
+
+    def two_way_sweep(self):
+        """the reference's own two_way_transport_sweep (solver.c:556-891)"""
+        return self.lib(self.variant).ref_two_way_transport_sweep(self.h)
 
     def time_sweep(self):
         return self.lib(self.variant).ref_time_transport_sweep(self.h)
