@@ -971,6 +971,8 @@ static int ensure_record_capacity(moc_handle *h, long long records)
 }
 
 static int exchange_on_stream(moc_handle *h, const CommGrid *grid, cudaStream_t st);   // comms section
+static int ensure_exchange_stage(moc_handle *h, long n_recv, long long chunk);
+static long exchange_receives(moc_handle *h, const CommGrid *grid, long long *chunk);
 
 // events of the per-batch pipeline, created on demand and kept for the next sweep
 static int event_at(moc_handle *h, size_t idx, cudaEvent_t *out)
@@ -1013,6 +1015,13 @@ static int sweep_core(moc_handle *h, long *segments_processed, const HostLayout 
         const long long floats = (long long)n_ops * 10000ll * h->G;              // comms.c:12-28: whole messages
         const long long tracks = (floats + 2ll * h->G - 1) / (2ll * h->G);       // [t][2][G] slab
         boundary_pairs = std::min<long long>((tracks + h->Z - 1) / h->Z, pairs);
+    }
+    if (overlap_grid && !io) {
+        // the exchange's receive staging comes first: the record buffers below take what is left
+        long long chunk = 0;
+        const long n_recv = exchange_receives(h, overlap_grid, &chunk);
+        if (n_recv < 0) return (int)n_recv;
+        if (n_recv > 0 && (rc = ensure_exchange_stage(h, n_recv, chunk))) return rc;
     }
     if (boundary_pairs > 0 && boundary_pairs < pairs) {
         chunk_first = {0, boundary_pairs, pairs};
@@ -1703,6 +1712,44 @@ static int allreduce_scalars(moc_handle *h, float *dev, int count)
     return MOC_OK;
 }
 
+// Receive staging of the boundary exchange: n_recv chunks.  On problems that fill the HBM (SURVEY config 5:
+// 129 GB of flux, 32 GB of staging at 2x2x2) the segment-record buffers of the last sweep may be in the
+// way: they are scratch, so they are given back and the allocation is tried again.
+static int ensure_exchange_stage(moc_handle *h, long n_recv, long long chunk)
+{
+    if (n_recv <= h->stage_chunks) return MOC_OK;
+    if (h->recv_stage) cudaFree(h->recv_stage);
+    h->recv_stage = nullptr;
+    h->stage_chunks = 0;
+    const size_t bytes = sizeof(float) * (size_t)n_recv * (size_t)chunk;
+    if (cudaMalloc((void **)&h->recv_stage, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        h->recv_stage = nullptr;
+        if (h->d.rec_ds) cudaFree(h->d.rec_ds);
+        if (h->d.rec_zin) cudaFree(h->d.rec_zin);
+        if (h->d.rec_code) cudaFree(h->d.rec_code);
+        h->d.rec_ds = h->d.rec_zin = nullptr;
+        h->d.rec_code = nullptr;
+        h->rec_capacity = 0;
+        CUDA_TRY(cudaMalloc((void **)&h->recv_stage, bytes));
+    }
+    h->stage_chunks = n_recv;
+    return MOC_OK;
+}
+
+// receives of one exchange under `grid` (chunks that arrive from a neighbour) and the chunk size in floats
+static long exchange_receives(moc_handle *h, const CommGrid *grid, long long *chunk)
+{
+    const long n_ops = moc_exchange_plan(&h->I, grid, nullptr, 0);
+    if (n_ops <= 0) return n_ops;
+    std::vector<moc_exchange_op> ops((size_t)n_ops);
+    moc_exchange_plan(&h->I, grid, ops.data(), n_ops);
+    long n_recv = 0;
+    for (const moc_exchange_op &op : ops) n_recv += op.recv_from >= 0;
+    *chunk = ops[0].count;
+    return n_recv;
+}
+
 // fast_transfer_boundary_fluxes (comms.c:5-196) on the device, driven by the host schedule
 // moc_exchange_plan() (moc_host.c).  Chunks sit at the head of the flux slab in (round,
 // direction) order.  Border faces: the chunk's pairwise sum goes to the leakage, zeros come
@@ -1748,12 +1795,8 @@ static int exchange_on_stream(moc_handle *h, const CommGrid *grid, cudaStream_t 
         CUDA_TRY(cudaMalloc((void **)&h->exch_sums, sizeof(float) * (size_t)n_ops));
         h->exch_capacity = n_ops;
     }
-    if (n_recv > h->stage_chunks) {
-        if (h->recv_stage) cudaFree(h->recv_stage);
-        h->recv_stage = nullptr;
-        CUDA_TRY(cudaMalloc((void **)&h->recv_stage, sizeof(float) * (size_t)n_recv * (size_t)chunk));
-        h->stage_chunks = n_recv;
-    }
+    int rc_stage = ensure_exchange_stage(h, n_recv, chunk);
+    if (rc_stage) return rc_stage;
     // The tables depend on the grid only: upload once.  (A pageable cudaMemcpyAsync synchronises the
     // host with the stream first -- the overlapped form must not wait for the boundary sweep here.)
     if (!h->exch_table_ready || memcmp(&h->exch_grid, grid, sizeof(CommGrid)) != 0 || h->exch_table_ops != n_ops) {
