@@ -459,6 +459,19 @@ def run_moc(args):
     elif l2_probe is not None:
         roof["l2"]["probe_error"] = l2_probe
     roof["frac"] = roof["achieved"] / hbm_peak if roof["achieved"] else None
+    # what the kernel is actually bound by: FMA-pipe occupancy from the static instruction mix of the
+    # G = 104 instantiation (per segment and lane of 13 groups, 210 packed FP32x2
+    # instructions at 2 pipe cycles + 60 scalar FFMA/FMUL/FADD/IMAD at 1) against 128 FP32 lanes per SM at
+    # the SM clock sampled during the timed region; ncu's sm__pipe_fma_cycles_active of the same kernel is
+    # the cross-check (profiles/r01_K1_attenuate_coef_ncu_full.txt)
+    if G == 104 and inp.axial_exp == 2 and clocks and clocks.get("sm_mhz") and att_s:
+        packed, scalar = (210, 60) if args.exp == "table" else (192, 45)
+        cycles = (2 * packed + scalar) / 13.0
+        n_sm = torch.cuda.get_device_properties(local).multi_processor_count
+        lanes_per_s = n_sm * 128 * clocks["sm_mhz"] * 1e6
+        roof["fp32"].update({"fma_pipe_lane_cycles_per_integration": cycles,
+                             "frac_of_fma_pipe": my_integ * cycles / att_s / lanes_per_s,
+                             "fma_pipe_peak": f"{n_sm} SMs x 128 lanes x {clocks['sm_mhz']:.0f} MHz (sampled)"})
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
