@@ -401,6 +401,27 @@ def run_moc(args):
     value = integrations / (ms * 1e-3)
 
     leakage = dev.leakage
+    # ---- the same step with the other exponential (north_star: MUFU.EX2 instead of the reference's table),
+    # two timed steps; informational: the headline `value` is the mode --exp names (default: parity mode)
+    other = None
+    if world == 1 and not args.limit_tracks_2d:
+        try:
+            dev.set_option(api.OPT_EXP_MODE, api.EXP_TABLE_REF if args.exp == "sfu" else api.EXP_SFU)
+            saved = dict(state)
+            step(False)
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            f0.record(stream)
+            n_other = step(False) + step(False)
+            f1.record(stream)
+            torch.cuda.synchronize()
+            o_ms = f0.elapsed_time(f1)
+            other = {"exp": "table" if args.exp == "sfu" else "sfu", "steps": 2, "ms_per_step": o_ms / 2,
+                     "value": n_other * G / (o_ms * 1e-3), "unit": UNIT,
+                     "attenuate_ms": dev.timing().attenuate_ms}
+            state.update(saved)
+        finally:
+            dev.set_option(api.OPT_EXP_MODE, exp_mode)
     # ---- the measured ceiling of K1's memory side (needs the resident handle: before the e2e leg)
     l2_probe = None
     try:
@@ -500,6 +521,7 @@ def run_moc(args):
                 "phases_ms": {"count": state["count_ms"] / n_launch, "fill": state["fill_ms"] / n_launch,
                               "attenuate": state["att_ms"] / n_launch},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roof, "e2e": e2e,
+                "other_exp_mode": other,
                 "cpu_baseline": cpu}
         if args.limit_tracks_2d:
             line["config"]["limit_tracks_2d"] = args.limit_tracks_2d
