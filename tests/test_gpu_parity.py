@@ -329,3 +329,15 @@ def test_dropin_names_on_the_reference_own_structures(built):
     L.moc_set_resident(0)
     assert L.moc_release(C.byref(params)) == 0
     mine.close(); theirs.close()
+
+
+def test_randomised_configurations(built):
+    """tools/fuzz_parity.py: 25 random small configurations (group counts 1..200, 1..300 rays per stack, flat
+    and quadratic source, both ray-trace kernels, overlapped emit, per-segment fit): integers bit-exact on two
+    sweeps, flux and k-eff within 1e-4 on the first."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz_parity.py"), "25", "3"],
+                       capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-2000:]
+    assert "25 cases, 0 mismatches" in p.stdout

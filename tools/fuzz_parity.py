@@ -1,0 +1,81 @@
+"""Randomised parity check of the CUDA path against the CPU oracle (diagnostic; the fixed cases live in tests/):
+python tools/fuzz_parity.py [n_cases] [seed]"""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np
+import simplemoc_b200 as m
+from simplemoc_b200 import api
+from oracle_lib import OracleCase, rel_l2, frac_within
+
+n_cases = int(sys.argv[1]) if len(sys.argv) > 1 else 30
+rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
+GROUPS = [1, 3, 4, 8, 10, 16, 32, 33, 64, 96, 100, 104, 128, 130, 200]
+bad = 0
+done = 0
+while done < n_cases:
+    xa, ya = int(rng.integers(2, 5)), int(rng.integers(2, 5))
+    cai, fai = int(rng.integers(1, 7)), int(rng.integers(3, 7))
+    axial_exp = int(rng.choice([2, 2, 2, 0]))
+    decompose = int(rng.integers(0, 2))
+    dax = int(rng.integers(1, 11)) if decompose else 1
+    height = 400.0
+    zs = int(rng.choice([1, 2, 3, 7, 25, 33, 64, 100, 129, 200, 300]))      # rays per stack wanted
+    node = height / dax if decompose else height
+    zsep = float(np.float32(node / zs * rng.uniform(0.95, 1.05)))
+    vals = [xa, ya, cai, fai, axial_exp, float(rng.uniform(1.5, 4.0)), zsep, int(rng.integers(4, 9)),
+            int(rng.integers(1, 7)), int(rng.choice(GROUPS)), decompose, dax, int(rng.integers(3, 16)), 21.42, height, 0.01,
+            int(rng.integers(80, 200)), 0]
+    inp = m.derive(m.input_from_values(vals))
+    work = inp.ntracks * (vals[12] + cai * fai) * vals[9]
+    if inp.ntracks <= 0 or inp.n_source_regions_per_node < 8 or work > 6e7 or inp.z_stacked > 2000:
+        continue
+    seed = int(rng.integers(1, 1000))
+    walk = int(rng.choice([0, 0, 1]))
+    try:
+        host = m.HostProblem(inp, seed=seed)
+        dev = m.DeviceProblem(host, device=0)
+        dev.set_option(api.OPT_DIGEST, 1)
+        if walk:
+            dev.set_option(api.OPT_WALK_KERNEL, 1)
+        if rng.integers(0, 4) == 0:
+            dev.set_option(api.OPT_FILL_OVERLAP, 1); dev.set_option(api.OPT_FILL_BATCHES, int(rng.integers(2, 6)))
+        if rng.integers(0, 4) == 0:
+            dev.set_option(api.OPT_FIT_PER_SEGMENT, 1)
+        ora = OracleCase(vals, seed=seed)
+        if ora.n_segments.min() < 0:
+            # a negative segment-count draw: the reference then lays its 2D segments out overlapping
+            # (tracks.c:29-47) -- undefined there, clamped to 0 here (tests/oracle_lib.py CASES "ragged")
+            print(f"[{done:3d}] skipped: negative n_segments draw (undefined in the reference)", flush=True)
+            dev.close(); host.close(); ora.close()
+            done += 1
+            continue
+        msgs = []
+        for sw in range(2):
+            n_g, n_c = dev.sweep(), ora.sweep()
+            if n_g != n_c: msgs.append(f"sweep{sw}: segments {n_g} != {n_c}")
+            if not np.array_equal(dev.get(api.ARR_SEG_COUNT), ora.seg_count): msgs.append(f"sweep{sw}: seg_count")
+            if not np.array_equal(dev.get(api.ARR_QSR_DIGEST), ora.digest): msgs.append(f"sweep{sw}: digest")
+            if not np.array_equal(dev.get(api.ARR_Z_HEIGHT), ora.z_height): msgs.append(f"sweep{sw}: z_height")
+            f, o = dev.get(api.ARR_FINE_FLUX), ora.fine_flux
+            e = rel_l2(f, o)
+            if sw == 0 and not (e <= 1e-4):
+                d = np.abs(f.astype(np.float64) - o)
+                worst = int(np.argmax(d))
+                msgs.append(f"sweep0: flux rel-L2 {e:.2e}, {frac_within(f, o, 1e-4):.5f} of elements within 1e-4; largest "
+                            f"difference at element {worst}: gpu {f.ravel()[worst]:.6e} oracle {o.ravel()[worst]:.6e}, "
+                            f"sum|tally| there {ora.abs_flux.ravel()[worst]:.3e}, max|flux| {np.abs(o).max():.3e}; vals={vals} seed={seed}")
+            dev.renormalize(); ora.renormalize()
+            dev.update_sources(1.0); ora.update_sources(1.0)
+            kg, kc = dev.compute_keff(), ora.compute_keff()
+            if sw == 0 and np.isfinite(kc) and abs(kg - kc) > 1e-4 * abs(kc): msgs.append(f"keff {kg} vs {kc}")
+        status = "ok" if not msgs else "MISMATCH " + "; ".join(msgs)
+        bad += bool(msgs)
+        print(f"[{done:3d}] T2={inp.ntracks_2D} P={inp.n_polar_angles} Z={inp.z_stacked} G={inp.n_egroups} cai={cai} fai={fai} exp={axial_exp} "
+              f"dax={dax} spt={vals[12]} walk={walk} segs={n_c}: {status}", flush=True)
+        dev.close(); host.close(); ora.close()
+    except m.MocError as e:
+        print(f"[{done:3d}] vals={vals}: library refused: {e}", flush=True)
+    done += 1
+print(f"{done} cases, {bad} mismatches")
+sys.exit(1 if bad else 0)
