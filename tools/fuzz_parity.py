@@ -69,7 +69,39 @@ while done < n_cases:
             dev.update_sources(1.0); ora.update_sources(1.0)
             kg, kc = dev.compute_keff(), ora.compute_keff()
             if sw == 0 and np.isfinite(kc) and abs(kg - kc) > 1e-4 * abs(kc): msgs.append(f"keff {kg} vs {kc}")
-        status = "ok" if not msgs else "MISMATCH " + "; ".join(msgs)
+        dropin = ""
+        if rng.integers(0, 3) == 0:
+            # the same problem through the drop-in names on HOST structures (non-resident: every call uploads
+            # and downloads in chunks of z-stacks), two iterations of main.c:57-92, a random chunk count
+            import ctypes as C
+            L = api.lib()
+            host2 = m.HostProblem(m.derive(m.input_from_values(vals)), seed=seed)
+            ora2 = OracleCase(vals, seed=seed)
+            L.moc_dropin_configure(seed, host2.rand_calls, 0, 48)
+            L.moc_set_resident(0)
+            grid = api.CommGrid(*([-1] * 12))
+            k = 1.0
+            chunks = int(rng.choice([1, 2, 5, 16, 40]))
+            for it in range(2):
+                L.transport_sweep(C.byref(host2.P), C.byref(host2.I))
+                if it == 0:
+                    L.moc_set_option(L.moc_handle_of(C.byref(host2.P)), api.OPT_STREAM_CHUNKS, chunks)
+                n_c = ora2.sweep()
+                if host2.I.segments_processed != n_c: msgs.append(f"drop-in it{it}: segments")
+                if not np.array_equal(host2.get(api.ARR_Z_HEIGHT), ora2.z_height): msgs.append(f"drop-in it{it}: z_height")
+                if it == 0:
+                    for name, a, b in (("flux", host2.get(api.ARR_FINE_FLUX), ora2.fine_flux), ("psi", host2.get(api.ARR_PSI), ora2.psi)):
+                        e = rel_l2(a, b)
+                        if not (e <= 1e-4): msgs.append(f"drop-in: {name} rel-L2 {e:.2e}")
+                L.renormalize_flux(host2.P, host2.I, grid); ora2.renormalize()
+                L.update_sources(host2.P, host2.I, k); ora2.update_sources(k)
+                kg, kc = L.compute_keff(host2.P, host2.I, grid), ora2.compute_keff()
+                if it == 0 and np.isfinite(kc) and abs(kg - kc) > 1e-4 * abs(kc): msgs.append(f"drop-in keff {kg} vs {kc}")
+                k = 1.0
+            L.moc_release(C.byref(host2.P))
+            host2.close(); ora2.close()
+            dropin = f" +drop-in({chunks} chunks)"
+        status = ("ok" if not msgs else "MISMATCH " + "; ".join(msgs)) + dropin
         bad += bool(msgs)
         print(f"[{done:3d}] T2={inp.ntracks_2D} P={inp.n_polar_angles} Z={inp.z_stacked} G={inp.n_egroups} cai={cai} fai={fai} exp={axial_exp} "
               f"dax={dax} spt={vals[12]} walk={walk} segs={n_c}: {status}", flush=True)
