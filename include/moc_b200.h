@@ -168,6 +168,11 @@ void fast_transfer_boundary_fluxes(Params params, Input I, CommGrid grid);
  * (48, or 56 when it was compiled with -DOPENMP).  Applies to mirrors created afterwards. */
 void moc_dropin_configure(unsigned long long seed, unsigned long long rand_base, int exp_mode,
                           int source_stride);
+/* A host program that is NOT edited (the reference's main.c linked as it is) never calls the function
+ * above.  If it -- or anything linked into it -- exports
+ *     void moc_host_rand_state(unsigned long long *seed, unsigned long long *calls);
+ * the library calls it (dlsym) when the first drop-in call builds the mirror, and takes the seed and
+ * position of the host's rand() stream from there.  oracle/dropin_glue.c is such an export. */
 /* CUDA device the drop-in names create their mirror on (cudaSetDevice) */
 int moc_set_device(int device);
 /* 1: keep results on the device between the calls above; 0 (default): write back */

@@ -21,6 +21,7 @@ static uint64_t g_calls = 0;
 
 void ref_shim_reset(uint64_t seed) { g_seed = seed; g_calls = 0; }
 uint64_t ref_shim_calls(void) { return g_calls; }
+uint64_t ref_shim_seed(void) { return g_seed; }
 void ref_shim_set_calls(uint64_t c) { g_calls = c; }
 
 int rand(void) { return (int)moc_rand31(g_seed, g_calls++); }

@@ -1894,6 +1894,7 @@ static std::mutex g_mirror_mutex;
 static std::unordered_map<const void *, Mirror> g_mirrors;   // keyed by Params.tracks
 static int g_resident = 0;
 static unsigned long long g_dropin_seed = 1, g_dropin_rand_base = 0;
+static bool g_dropin_configured = false;
 static int g_dropin_exp_mode = 0, g_dropin_source_stride = 48;
 static CommGrid g_dropin_grid;
 static bool g_dropin_grid_set = false;
@@ -1920,6 +1921,7 @@ extern "C" int moc_set_device(int device)
 extern "C" void moc_dropin_configure(unsigned long long seed, unsigned long long rand_base, int exp_mode,
                                      int source_stride)
 {
+    g_dropin_configured = true;
     g_dropin_seed = seed;
     g_dropin_rand_base = rand_base;
     g_dropin_exp_mode = exp_mode;
@@ -1977,6 +1979,18 @@ static Mirror &mirror_for(const Params *P, const Input *I, HostLayout &L, bool n
         m.h->seed = g_dropin_seed;
         m.h->rand_base = g_dropin_rand_base;
         m.h->exp_mode = g_dropin_exp_mode;
+        if (!g_dropin_configured) {
+            // A host program that cannot be edited to call moc_dropin_configure (the reference's own main.c,
+            // linked unmodified) may export  void moc_host_rand_state(unsigned long long *seed,
+            // unsigned long long *calls)  instead: where ITS rand() stream stands at the first sweep.
+            typedef void (*rand_state_fn)(unsigned long long *, unsigned long long *);
+            if (rand_state_fn f = (rand_state_fn)dlsym(RTLD_DEFAULT, "moc_host_rand_state")) {
+                unsigned long long seed = g_dropin_seed, calls = g_dropin_rand_base;
+                f(&seed, &calls);
+                m.h->seed = seed;
+                m.h->rand_base = calls;
+            }
+        }
         created = true;
     } else if (inspect_layout(I, P, m.h->source_stride, L)) {
         die(where);

@@ -63,3 +63,28 @@ def test_driver_reports_what_the_oracle_computes(built, tmp_path, case, extra, t
     if track_file:
         assert "Reading track data from" in out and "2D tracks:" in out
     o.close()
+
+
+REF_MAIN = os.path.join(ROOT, "oracle", "_ref", "SimpleMOC-dropin")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case,seed", [("tiny", 11), ("mini104", 4), ("tiny_flat", 7)])
+def test_the_reference_own_main_linked_against_the_library(built, tmp_path, case, seed):
+    """oracle/_ref/SimpleMOC-dropin = the reference's main.c, init.c, io.c, tracks.c, source.c, utils.c --
+    unmodified -- with solver.c and comms.c replaced by libmoc_b200.so (oracle/Makefile `dropin`).  It prints
+    the k-eff the all-CPU reference computes from the same pinned random stream."""
+    from oracle_lib import RefCase, ref_available
+    if not (os.path.exists(REF_MAIN) and ref_available()):
+        pytest.skip("oracle/_ref/SimpleMOC-dropin did not travel")
+    f = write_input_file(str(tmp_path / f"{case}.in"), CASES[case])
+    p = subprocess.run([REF_MAIN, "-i", f], capture_output=True, text=True, timeout=600,
+                       env=dict(os.environ, SMOC_SEED=str(seed)))
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+    k_gpu = float(re.search(r"^keff = (\S+)", p.stdout, flags=re.M).group(1))
+    r = RefCase(CASES[case], seed=seed)
+    r.sweep(); r.renormalize(); r.update_sources(1.0)
+    k_cpu = r.compute_keff()
+    assert abs(k_gpu - k_cpu) <= 1e-4 * abs(k_cpu) + 5e-7, (k_gpu, k_cpu)
+    assert "Time per Intersection" in p.stdout          # the reference's own report (main.c:130-134)
+    r.close()
