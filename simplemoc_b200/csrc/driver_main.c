@@ -13,7 +13,8 @@
  * New long options (none of them changes what the old ones mean):
  *   --seed N          counter-RNG seed (the reference seeds from time(NULL), src/main.c:20)
  *   --exp table|sfu   exponential: the reference's table (default) or MUFU.EX2
- *   --iters N         iterations of the loop (the reference hard-codes 1, src/main.c:41)
+ *   --iters N         iterations of the loop (the reference hard-codes 1, src/main.c:41); N > 1 also
+ *                     prints the source residual update_sources returns (dropped by main.c:81)
  *   --host-buffers    strict drop-in mode: every phase uploads from / downloads to the host
  *                     structures; default keeps the problem resident in HBM between phases and
  *                     synchronises the host structures once at the end
@@ -177,9 +178,11 @@ int main(int argc, char *argv[])
         b = now();
         t_keff += b - a;
         if (rank == 0) printf("keff = %f\n", keff);
+        /* the reference computes the source residual and drops it (main.c:81); with more than the
+         * reference's single iteration it is what tells whether the source iteration converges */
+        if (rank == 0 && iters > 1) printf("iteration %d: source residual = %.6e\n", it + 1, res);
     }
     if (!host_buffers && moc_sync_to_host(&params)) die("sync to host");
-    (void)res;
 
     const double total = t_sweep + t_exch + t_renorm + t_update + t_keff;
     if (rank == 0) {

@@ -57,6 +57,7 @@ def test_driver_reports_what_the_oracle_computes(built, tmp_path, case, extra, t
     assert int(re.search(r"Segments processed:\s+(\d+)", out).group(1)) == segs
     printed = [float(x) for x in re.findall(r"^keff = (\S+)", out, flags=re.M)]
     assert len(printed) == iters
+    assert len(re.findall(r"source residual = ", out)) == (iters if iters > 1 else 0)
     for a, b in zip(printed, ks):
         assert abs(a - b) <= 1e-4 * abs(b) + 5e-7, (printed, ks)      # "%f" prints six decimals
     assert f"3D tracks:" in out and str(o.I.ntracks) in out
