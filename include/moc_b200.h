@@ -214,8 +214,9 @@ enum {
     MOC_OPT_LANES_PER_TRACK = 6,/* override the lane mapping of the attenuation kernel (0=auto)  */
     MOC_OPT_STREAM_CHUNKS = 7,  /* z-stack chunks the host-side transport_sweep moves the angular
                                    flux in (copies overlap kernels), default 16                  */
-    MOC_OPT_WALK_KERNEL = 8,    /* axial ray trace: 0 = auto, 1 = one CTA per z-stack, 2 = one
-                                   warp per z-stack (needs z_stacked <= 128)                     */
+    MOC_OPT_WALK_KERNEL = 8,    /* axial ray trace: 0 = auto (warps per z-stack: one for z_stacked <= 128,
+                                   ceil(z_stacked / 128) up to 2048; one thread per ray above),
+                                   1 = always one thread per ray, 2 = same as 0                  */
     MOC_OPT_FILL_OVERLAP = 9,   /* ray-trace CTAs per SM that emit the segment records of batch b+1
                                    under the attenuation of batch b (0 = emit in front of it);
                                    warp-per-stack ray trace only.  Default 0: same sweep time on

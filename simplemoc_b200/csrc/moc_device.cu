@@ -826,6 +826,27 @@ static void launch_walk(const moc_handle *h, const WalkParams &w, long long n_pa
 #undef MOC_WALK
         return;
     }
+    if (h->walk_kernel != 1 && Z <= 2048) {
+        // taller stacks: the same walk with ceil(Z / 128) warps per stack (one CTA per stack and direction)
+        const long long P = h->P, H = P / 2, p0 = w.first_pair, p1 = w.first_pair + n_pairs;
+        auto ups_before = [&](long long p) { return (p / P) * H + std::min<long long>(p % P, H); };
+        const long long up0 = ups_before(p0), n_up = ups_before(p1) - up0;
+        const long long down0 = p0 - up0, n_down = n_pairs - n_up;
+        const unsigned threads = 32u * (unsigned)((Z + 127) / 128);
+        const bool fast = h->iv_fast && h->fine_fast;
+#define MOC_WALK_BLOCK(UP, before, n)                                                                          \
+    if ((n) > 0) {                                                                                              \
+        unsigned grid = (unsigned)std::min<long long>((n), 0x7fffffffll);                                       \
+        if (max_ctas && grid > max_ctas) grid = max_ctas;                                                       \
+        if (fast) stack_walk_block_kernel<FILL, UP, true><<<grid, threads, 0, st>>>(w, before, n);              \
+        else stack_walk_block_kernel<FILL, UP, false><<<grid, threads, 0, st>>>(w, before, n);                  \
+        h->launch_count++;                                                                                      \
+    }
+        MOC_WALK_BLOCK(true, up0, n_up)
+        MOC_WALK_BLOCK(false, down0, n_down)
+#undef MOC_WALK_BLOCK
+        return;
+    }
     int kpt = 1;
     while (kpt < 16 && (Z + kpt - 1) / kpt > 256) kpt *= 2;
     int threads = ((Z + kpt - 1) / kpt + 31) / 32 * 32;

@@ -168,17 +168,23 @@ __device__ __forceinline__ void put(T (&v)[KPT], int r, T x)
     for (int q = 0; q < KPT; q++) v[q] = (r == q) ? x : v[q];
 }
 
-template <int KPT, bool FILL, bool UP, bool FAST>
+// BLOCK = false: the stack belongs to ONE warp (Z <= 32 KPT).  BLOCK = true: to the blockDim.x / 32 warps of a
+// CTA (Z <= blockDim.x KPT): same per-lane work, the stack-wide prefixes and totals cross the warps through
+// `xw` (2 x 33 u64 of shared memory) and two __syncthreads per 2D segment.
+template <int KPT, bool FILL, bool UP, bool FAST, bool BLOCK>
 __device__ __forceinline__ void walk_stack_warp(const WalkParams &w, const long long pair, const long long local,
-                                                const long long i, const int j, const int lane)
+                                                const long long i, const int j, const int lane,
+                                                unsigned long long *xw = nullptr)
 {
+    const int warp = BLOCK ? (int)(threadIdx.x >> 5) : 0;
+    const int n_warps = BLOCK ? (int)(blockDim.x >> 5) : 1;
     const int Z = w.Z;
     const int n_seg = w.n_seg[i];
     const float *len = w.seg_len + w.seg_start[i];
     const double cos_p = w.cos_p[j], sin_p = w.sin_p[j];
     const double rcos = __ddiv_rn(1.0, cos_p);
     const long long t0 = pair * Z;
-    const int k0 = lane * KPT;
+    const int k0 = (warp * 32 + lane) * KPT;
 
     float zh[KPT];
     uint32_t made_total[KPT];          // count pass: segments of the ray so far
@@ -309,6 +315,15 @@ __device__ __forceinline__ void walk_stack_warp(const WalkParams &w, const long 
             cnt_before = ex & 0xffffffu;
             exits_before = ex >> 24;
         }
+        if (BLOCK) {
+            // warp totals -> shared memory -> every thread adds the totals of the warps below its own
+            if (lane == 31) xw[warp] = ((unsigned long long)(exits_before + lane_exits) << 32) | (cnt_before + lane_cnt);
+            __syncthreads();
+            unsigned long long below = 0;
+            for (int q = 0; q < warp; q++) below += xw[q];
+            cnt_before += (uint32_t)below;
+            exits_before += (uint32_t)(below >> 32);
+        }
 
         // ---- who is really processed: upward rays see end_stacked shrink as lower rays exit
         uint32_t taken_cnt = 0, taken_exits = 0, taken = 0;
@@ -370,8 +385,17 @@ __device__ __forceinline__ void walk_stack_warp(const WalkParams &w, const long 
                 else made_total[r] += cnt[r];
             }
         }
-        const uint32_t done_exits = __reduce_add_sync(0xffffffffu, taken_exits);
-        const uint32_t done_cnt = __reduce_add_sync(0xffffffffu, taken_cnt);
+        uint32_t done_exits = __reduce_add_sync(0xffffffffu, taken_exits);
+        uint32_t done_cnt = __reduce_add_sync(0xffffffffu, taken_cnt);
+        if (BLOCK) {
+            // second exchange: what the warps really processed (the first one's slots are still being read)
+            if (lane == 0) xw[33 + warp] = ((unsigned long long)done_exits << 32) | done_cnt;
+            __syncthreads();
+            unsigned long long all = 0;
+            for (int q = 0; q < n_warps; q++) all += xw[33 + q];
+            done_cnt = (uint32_t)all;
+            done_exits = (uint32_t)(all >> 32);
+        }
         if (UP) hi -= (int)done_exits;
         else lo += (int)done_exits;
         serial_at += done_cnt;
@@ -411,7 +435,23 @@ __device__ __forceinline__ void walk_stack_warp(const WalkParams &w, const long 
 #pragma unroll
         for (int r = 0; r < KPT; r++) longest = max(longest, made_total[r]);
         longest = __reduce_max_sync(0xffffffffu, longest);
-        if (lane == 0) {
+        if (BLOCK) {
+            __syncthreads();   // the last step's exchange has been read by everybody
+            if (lane == 0) {
+                xw[warp] = tot;
+                xw[33 + warp] = longest;
+            }
+            __syncthreads();
+            if (warp == 0 && lane == 0) {
+                unsigned long long t = 0, l = 0;
+                for (int q = 0; q < n_warps; q++) {
+                    t += xw[q];
+                    l = xw[33 + q] > l ? xw[33 + q] : l;
+                }
+                w.pair_count[pair] = t;
+                w.pair_max[pair] = (uint32_t)l;
+            }
+        } else if (lane == 0) {
             w.pair_count[pair] = tot;
             w.pair_max[pair] = longest;   // the longest ray decides how many record rows the stack needs
         }
@@ -436,6 +476,23 @@ __global__ void __launch_bounds__(128) stack_walk_warp_kernel(const WalkParams w
         const long long i = target / per_track;
         const int j = (int)(target - i * per_track) + (UP ? 0 : H);
         const long long pair = i * w.P + j;
-        walk_stack_warp<KPT, FILL, UP, FAST>(w, pair, pair - w.first_pair, i, j, lane);
+        walk_stack_warp<KPT, FILL, UP, FAST, false>(w, pair, pair - w.first_pair, i, j, lane);
+    }
+}
+
+// Taller stacks (128 < Z <= 2048): one CTA of ceil(Z / 128) warps per stack, four rays per lane, the same walk.
+template <bool FILL, bool UP, bool FAST>
+__global__ void __launch_bounds__(512) stack_walk_block_kernel(const WalkParams w, long long dir_before, long long n_dir)
+{
+    __shared__ unsigned long long xw[66];
+    const int lane = threadIdx.x & 31;
+    const int H = w.P / 2, per_track = UP ? H : w.P - H;
+    for (long long q = blockIdx.x; q < n_dir; q += gridDim.x) {
+        const long long target = dir_before + q;
+        const long long i = target / per_track;
+        const int j = (int)(target - i * per_track) + (UP ? 0 : H);
+        const long long pair = i * w.P + j;
+        walk_stack_warp<4, FILL, UP, FAST, true>(w, pair, pair - w.first_pair, i, j, lane, xw);
+        __syncthreads();   // xw is reused by the next stack
     }
 }
