@@ -7,9 +7,12 @@ import simplemoc_b200 as m
 from simplemoc_b200 import api
 
 exp_mode = int(sys.argv[1]) if len(sys.argv) > 1 else 0
-inp = m.derive(m.default_input())
+inp = m.default_input()
+if len(sys.argv) > 2:
+    inp.n_egroups = int(sys.argv[2])          # python tools/probe_overlap.py <exp_mode> <G>
+inp = m.derive(inp)
 dev = m.DeviceProblem.synthetic(inp, seed=1, device=0, exp_mode=exp_mode)
-for ctas, batches in ((0, 8), (1, 8), (2, 8), (1, 16), (2, 16), (3, 8), (1, 4), (0, 8)):
+for ctas, batches in ((0, 8), (1, 8), (2, 8), (3, 8), (4, 8), (2, 16), (0, 8)):
     dev.set_option(api.OPT_FILL_OVERLAP, ctas)
     dev.set_option(api.OPT_FILL_BATCHES, batches)
     res = []
