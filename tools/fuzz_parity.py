@@ -8,6 +8,20 @@ import simplemoc_b200 as m
 from simplemoc_b200 import api
 from oracle_lib import OracleCase, rel_l2, frac_within
 
+def keff_tolerance(ora, inp):
+    """1e-4, unless the k-eff of this random problem is ill-conditioned: k = F / A with F and A sums over the
+    signed scalar flux (solver.c:1324-1437); when a sum cancels to 1/kappa of its terms, flux differences of
+    ~1e-6 show up kappa times larger in k (seen: kappa_A = 3145, k = -487, 2.5e-4 off)."""
+    G, F, N = inp.n_egroups, inp.fai, inp.n_source_regions_per_node
+    flux = ora.fine_flux.reshape(N, F, G).astype(np.float64)
+    xs = ora.xs.reshape(-1, G, 3).astype(np.float64)[ora.xs_index]
+    kappa = 0.0
+    for col in (0, 1):
+        terms = flux * xs[:, None, :, col]
+        kappa += np.abs(terms).sum() / max(abs(terms.sum()), 1e-300)
+    return max(1e-4, 2e-6 * kappa)
+
+
 n_cases = int(sys.argv[1]) if len(sys.argv) > 1 else 30
 rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
 GROUPS = [1, 3, 4, 8, 10, 16, 32, 33, 64, 96, 100, 104, 128, 130, 200]
@@ -68,7 +82,8 @@ while done < n_cases:
             dev.renormalize(); ora.renormalize()
             dev.update_sources(1.0); ora.update_sources(1.0)
             kg, kc = dev.compute_keff(), ora.compute_keff()
-            if sw == 0 and np.isfinite(kc) and abs(kg - kc) > 1e-4 * abs(kc): msgs.append(f"keff {kg} vs {kc}")
+            if sw == 0 and np.isfinite(kc) and abs(kg - kc) > keff_tolerance(ora, inp) * abs(kc):
+                msgs.append(f"keff {kg} vs {kc} (tolerance {keff_tolerance(ora, inp):.1e})")
         dropin = ""
         if rng.integers(0, 3) == 0:
             # the same problem through the drop-in names on HOST structures (non-resident: every call uploads
@@ -96,7 +111,8 @@ while done < n_cases:
                 L.renormalize_flux(host2.P, host2.I, grid); ora2.renormalize()
                 L.update_sources(host2.P, host2.I, k); ora2.update_sources(k)
                 kg, kc = L.compute_keff(host2.P, host2.I, grid), ora2.compute_keff()
-                if it == 0 and np.isfinite(kc) and abs(kg - kc) > 1e-4 * abs(kc): msgs.append(f"drop-in keff {kg} vs {kc}")
+                if it == 0 and np.isfinite(kc) and abs(kg - kc) > keff_tolerance(ora2, host2.I) * abs(kc):
+                    msgs.append(f"drop-in keff {kg} vs {kc}")
                 k = 1.0
             L.moc_release(C.byref(host2.P))
             host2.close(); ora2.close()
