@@ -443,6 +443,18 @@ def run_moc(args):
     # algorithmic HBM bytes of one launch: angular flux in and out once, segment records in,
     # per-track offsets/counts/weights in (the gathered source rows live in L2)
     hbm_bytes = (2 * 4 * T3 * G + 12 * (state["segments"] / n_launch) + 12 * T3)
+    # Source slabs larger than the L2 (SURVEY config 5): the per-integration gathers (16 B read + 8 B
+    # read-modify-write) are DRAM traffic too, except for the share of the working set the L2
+    # can hold; the kernel then really is HBM-bound and `frac` is its HBM fraction
+    gather_note = None
+    Gp = (G + 31) // 32 * 32
+    gather_set = 4.0 * (2 * inp.fai + 1) * inp.n_source_regions_per_node * Gp
+    l2_size = float(torch.cuda.get_device_properties(local).L2_cache_size)
+    if inp.axial_exp == 2 and dev.get_option(api.OPT_FIT_PER_SEGMENT) == 1 and gather_set > l2_size:
+        miss = 1.0 - l2_size / gather_set
+        hbm_bytes += L2_BYTES_PER_INTEGRATION * miss * (my_integ / n_launch)
+        gather_note = (f"gather working set {gather_set / 1e6:.0f} MB > L2 {l2_size / 1e6:.0f} MB: "
+                       f"{L2_BYTES_PER_INTEGRATION} B/integration x {miss:.2f} counted as HBM traffic")
     hbm_peak, peak_src = measured_peaks()
     att_per_launch = att_s / n_launch
     # DRAM bytes of one launch from the committed ncu capture of this workload (profiles/), if there is one
@@ -467,7 +479,7 @@ def run_moc(args):
                      "flop_per_integration": FLOP_PER_INTEGRATION},
             "l2": {"achieved_gbs": my_integ * L2_BYTES_PER_INTEGRATION / att_s / 1e9 if att_s else None,
                    "bytes_per_integration": L2_BYTES_PER_INTEGRATION},
-            "note": "not HBM-bound: FP32 issue + L2 gather/atomic bound (DESIGN.md 'roofline')"}
+            "note": gather_note or "not HBM-bound: FP32 issue + L2 gather/atomic bound (DESIGN.md 'roofline')"}
     # the measured ceiling of the kernel's memory side: the same gathers + vector reductions on the
     # same (L2-resident) slab without the arithmetic, timed live (moc_probe_l2_gather)
     if isinstance(l2_probe, tuple):
