@@ -146,7 +146,7 @@ struct moc_handle {
     unsigned int walk_flags_host = 0;
     int iv_fast = 0, fine_fast = 0;   // interval_check_kernel found no mismatch (moc_walk_warp.cuh)
     float iv_lo = 0.f, iv_hi = 0.f;
-    int walk_kernel = 0;           // 0 = auto, 1 = one CTA per z-stack, 2 = one warp per z-stack (Z <= 128)
+    int walk_kernel = 0;           // 0 / 2 = warp(s) per z-stack (Z <= 2048), 1 = always one thread per ray
     // ray-trace CTAs per SM resident under the attenuation of the previous batch.  0 = off, the default:
     // measured on the default problem the overlapped sweep takes the same time (400 vs 398-408 ms,
     // profiles/r01_fill_overlap.log) -- the chip runs at its power cap, so hiding one kernel under the

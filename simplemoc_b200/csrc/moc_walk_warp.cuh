@@ -1,11 +1,14 @@
-/* moc_walk_warp.cuh -- K0 for short z-stacks (Z <= 32 * KPT, KPT <= 4): one WARP per
- * (2D track, polar angle) z-stack, lane l owns the KPT consecutive rays k = l*KPT .. +KPT-1.
+/* moc_walk_warp.cuh -- K0, the axial ray trace: one WARP per (2D track, polar angle) z-stack for
+ * Z <= 32 * KPT (KPT <= 4: stack_walk_warp_kernel), ceil(Z / 128) warps of one CTA per stack for
+ * 128 < Z <= 2048 (stack_walk_block_kernel); lane l of warp q owns the KPT consecutive rays
+ * k = (32 q + l) * KPT .. +KPT-1.
  * Included by moc_kernels.cuh inside namespace moc.  Same contract as stack_walk_kernel
  * (reference src/solver.c:347-529; window semantics SURVEY A.3), different mapping:
  *
- *   - no shared memory and no __syncthreads: the per-step prefix over the stack (exits below a
- *     ray, segments below a ray) is ONE 32-bit warp shuffle scan of a packed (exits | segments)
- *     word, the step totals are two REDUX instructions;
+ *   - the per-step prefix over the stack (exits below a ray, segments below a ray) is ONE 32-bit
+ *     warp shuffle scan of a packed (exits | segments) word, the step totals are two REDUX
+ *     instructions; the one-warp form needs no shared memory and no __syncthreads, the
+ *     several-warp form passes the warps' totals through 66 words of shared memory;
  *   - one launch per ray direction (upward / downward), the direction is a template parameter:
  *     no per-ray direction branches and only one instantiation resident in the instruction caches;
  *   - rays that stay inside their fine axial interval for the whole 2D segment are handled
