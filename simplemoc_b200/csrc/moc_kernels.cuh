@@ -610,6 +610,109 @@ __global__ void update_sources_kernel(const SourceParams p, float inverse_k, flo
     }
 }
 
+// A lane's place in the pairwise_sum tree over n terms when 2^depth lanes share one sum: lane `sub` owns the
+// leaf reached by descending with its bits (most significant first; a node of <= 16 terms is a leaf, as in
+// utils.c:29-45); split_mask bit l = the node `sub` stands for at level l really has two children.
+struct TreeSlot {
+    int lo, sz;          // the leaf [lo, lo + sz) -- summed sequentially by its owner
+    bool owner;          // this lane computes that leaf (the other lanes below an early leaf idle)
+    unsigned split_mask;
+};
+__device__ __forceinline__ TreeSlot tree_slot(int n, int depth, int sub)
+{
+    TreeSlot t;
+    t.lo = 0; t.sz = n; t.split_mask = 0;
+    int level = 0;
+    for (; level < depth; level++) {
+        if (t.sz <= 16) break;
+        t.split_mask |= 1u << level;
+        const int half = t.sz / 2;
+        if ((sub >> (depth - 1 - level)) & 1) { t.lo += half; t.sz -= half; }
+        else t.sz = half;
+    }
+    t.owner = (sub & ((1 << (depth - level)) - 1)) == 0;
+    return t;
+}
+// combine the leaves of 2^depth consecutive lanes in the recursion's own order: left + right at every node
+__device__ __forceinline__ float tree_combine(float v, const TreeSlot &t, int depth, int sub)
+{
+    for (int level = depth - 1; level >= 0; level--) {
+        const int span = 1 << (depth - level);
+        const float right = __shfl_down_sync(0xffffffffu, v, span / 2, 1 << depth);
+        // the node at `level` above this lane: split iff this lane descended through it
+        if ((sub & (span - 1)) == 0 && ((t.split_mask >> level) & 1u)) v = __fadd_rn(v, right);
+    }
+    return v;
+}
+__host__ __device__ __forceinline__ int tree_depth(int n)
+{
+    int d = 0;
+    while (n > 16) { n -= n / 2; d++; }
+    return d;
+}
+
+// update_sources_kernel with every 104-term (G-term) sum spread over 2^depth lanes: each lane sums one leaf
+// of <= 16 terms, the leaves are combined with shuffles in the order of the serial recursion -- the same
+// additions in the same order (bit-identical), a sixth of the dependent chain.  One CTA of 256 threads per
+// (region, fine interval); needs depth <= 5 (G <= 512).  dynamic shared memory: 2*G + 1 floats.
+__global__ void update_sources_coop_kernel(const SourceParams p, float inverse_k, float *fine_residual, int depth)
+{
+    extern __shared__ float sh[];
+    float *phi = sh;
+    float *res_g = sh + p.G;
+    float *fission_s = sh + 2 * p.G;
+    const long long row = blockIdx.x;
+    const long long i = row / p.fai;
+    const int G = p.G;
+    const float *flux = p.fine_flux + (size_t)row * p.pitch;
+    float *q = p.fine_source + (size_t)row * p.pitch;
+    const int material = p.xs_index[i];
+    const float *x = p.xs + (size_t)material * G * 3;
+    const float *S = p.scatter + (size_t)material * G * G;
+    const int lanes = 1 << depth, sub = threadIdx.x & (lanes - 1), group = threadIdx.x >> depth;
+    const int n_groups = blockDim.x >> depth;
+    const TreeSlot t = tree_slot(G, depth, sub);
+    for (int g = threadIdx.x; g < G; g += blockDim.x) phi[g] = flux[g];
+    __syncthreads();
+    {
+        // every group forms the fission sum (whole warps take part in the shuffles), group 0 publishes it
+        float v = 0.f;
+        if (t.owner)
+            for (int e = 0; e < t.sz; e++) v = __fadd_rn(v, __fmul_rn(phi[t.lo + e], x[3 * (t.lo + e)]));
+        v = tree_combine(v, t, depth, sub);
+        if (group == 0 && sub == 0) *fission_s = __fmul_rn(v, inverse_k);
+    }
+    __syncthreads();
+    const float fission = *fission_s;
+    for (int g0 = 0; g0 < G; g0 += n_groups) {       // uniform trip count: the shuffles need whole groups
+        const int g = g0 + group;
+        const bool live = g < G;
+        float v = 0.f;
+        if (live && t.owner) {
+            const float *Srow = S + (size_t)g * G + t.lo;
+            for (int e = 0; e < t.sz; e++) v = __fadd_rn(v, __fmul_rn(Srow[e], phi[t.lo + e]));
+        }
+        v = tree_combine(v, t, depth, sub);
+        if (live && sub == 0) {
+            const float chi = x[3 * g + 2];
+            const float mix = __fadd_rn(__fmul_rn(fission, chi), v);
+            const float fresh = (float)((double)mix / (4.0 * 3.14159265358979323846));
+            const float old = q[g];
+            const float d = __fsub_rn(fresh, old);
+            res_g[g] = __fdiv_rn(__fmul_rn(d, d), __fmul_rn(old, old));
+            q[g] = fresh;
+        }
+    }
+    __syncthreads();
+    {
+        float v = 0.f;
+        if (t.owner)
+            for (int e = 0; e < t.sz; e++) v = __fadd_rn(v, res_g[t.lo + e]);
+        v = tree_combine(v, t, depth, sub);
+        if (group == 0 && sub == 0) fine_residual[row] = v;
+    }
+}
+
 // per_region[i] = pairwise_sum(fine[i*fai .. +fai))
 __global__ void region_fold_kernel(const float *fine, long long N, int fai, float *per_region)
 {

@@ -52,8 +52,15 @@ extern "C" int moc_update_sources(moc_handle *h, float keff, float *res)
     const float inverse_k = (float)(1.0 / (double)keff);   // solver.c:1241
     const long long rows = h->N * h->F;
     const int threads = std::min(128, (h->G + 31) / 32 * 32);
-    update_sources_kernel<<<(unsigned)rows, threads, sizeof(float) * 2 * (size_t)h->G, h->stream>>>(
-        p, inverse_k, h->d.per_fine);
+    const int depth = tree_depth(h->G);
+    if (depth <= 5) {
+        // the G-term sums of a row spread over 2^depth lanes each (same tree, same order of additions)
+        update_sources_coop_kernel<<<(unsigned)rows, 256, sizeof(float) * (2 * (size_t)h->G + 1), h->stream>>>(
+            p, inverse_k, h->d.per_fine, depth);
+    } else {
+        update_sources_kernel<<<(unsigned)rows, threads, sizeof(float) * 2 * (size_t)h->G, h->stream>>>(
+            p, inverse_k, h->d.per_fine);
+    }
     region_fold_kernel<<<(unsigned)((h->N + 127) / 128), 128, 0, h->stream>>>(h->d.per_fine, h->N, h->F,
                                                                              h->d.per_region_a);
     pairwise_reduce_kernel<<<1, 256, 0, h->stream>>>(h->d.per_region_a, h->N, h->d.scalars, 1);

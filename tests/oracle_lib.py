@@ -78,6 +78,11 @@ CASES = {
     "polar2": [3, 3, 2, 3, 2, 2.0, 8.0, 8, 2, 12, 0, 1, 10, 21.42, 400.0, 0.01, 200, 0],
     "onecell": [3, 3, 1, 3, 2, 2.0, 4.0, 8, 4, 16, 0, 1, 10, 21.42, 400.0, 0.01, 200, 0],
     "zone": [3, 3, 4, 3, 2, 2.0, 400.0, 8, 4, 16, 0, 1, 10, 21.42, 400.0, 0.01, 200, 0],
+    # group counts whose pairwise_sum trees are uneven (utils.c:29-45: 33 = 16 + 17 -> 17 = 8 + 9;
+    # 130 = 65 + 65 -> 32 + 33 -> ...; 200): the reductions spread those trees over lanes
+    "g33": [3, 3, 3, 4, 2, 2.5, 8.0, 6, 2, 33, 0, 1, 6, 21.42, 400.0, 0.01, 96, 0],
+    "g130": [3, 3, 3, 3, 2, 2.5, 10.0, 6, 2, 130, 0, 1, 5, 21.42, 400.0, 0.01, 96, 0],
+    "g200": [3, 3, 2, 3, 2, 3.0, 16.0, 6, 2, 200, 0, 1, 4, 21.42, 400.0, 0.01, 96, 0],
     # 96 000 short 3D tracks, G=8: large enough for one 10 000-track message per face
     # (comms.c:12-28), cheap to sweep -- the boundary-exchange case
     "exch": [3, 3, 4, 3, 2, 2.0, 0.05, 8, 4, 8, 1, 20, 10, 21.42, 400.0, 0.01, 200, 0],

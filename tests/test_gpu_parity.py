@@ -96,10 +96,12 @@ def test_sweep_table_mode(built, case):
     dev.close(); host.close(); oracle.close()
 
 
-def test_reductions_bit_exact_on_identical_flux(built):
+@pytest.mark.parametrize("case", ["mini104", "tiny", "odd", "mini_default_in", "g33", "g130", "g200"])
+def test_reductions_bit_exact_on_identical_flux(built, case):
     """With the oracle's flux uploaded, renormalise / update / keff reproduce the
-    reference's pairwise_sum trees exactly (utils.c:29-45)."""
-    host, dev, oracle = make_pair("mini104", seed=5)
+    reference's pairwise_sum trees exactly (utils.c:29-45) -- for even and uneven trees (G = 104, 16, 10,
+    100, 33, 130, 200): update_sources spreads every G-term sum over up to 32 lanes."""
+    host, dev, oracle = make_pair(case, seed=5)
     oracle.sweep()
     dev.set(api.ARR_FINE_FLUX, oracle.fine_flux)
     dev.set(api.ARR_PSI, oracle.psi)
