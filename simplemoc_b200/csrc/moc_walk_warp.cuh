@@ -32,6 +32,16 @@
  */
 #pragma once
 
+// Both on by default; 0 restores the per-lane forms (kept for A/B timing: tools/gpu_runs).
+#ifndef MOC_WALK_COMPACT_CROSSING
+#define MOC_WALK_COMPACT_CROSSING 1
+#endif
+#ifndef MOC_WALK_STAGED_HASH
+#define MOC_WALK_STAGED_HASH 1
+#endif
+// per-warp shared-memory scratch of the walk: 128 crossing rays x 16 bytes, or 512 source regions
+#define WALK_SCRATCH_BYTES 2048
+
 // x % m.n for x < 2^31:  q = (x * magic) >> (32 + shift)   (Granlund-Montgomery, n = 31 bits)
 __device__ __forceinline__ uint32_t fastmod31(uint32_t x, uint32_t n, uint32_t magic, uint32_t shift)
 {
@@ -177,8 +187,11 @@ __device__ __forceinline__ void put(T (&v)[KPT], int r, T x)
 template <int KPT, bool FILL, bool UP, bool FAST, bool BLOCK>
 __device__ __forceinline__ void walk_stack_warp(const WalkParams &w, const long long pair, const long long local,
                                                 const long long i, const int j, const int lane,
-                                                unsigned long long *xw = nullptr)
+                                                uint4 *scratch, unsigned long long *xw = nullptr)
 {
+    // `scratch` (one warp per stack only): this warp's WALK_SCRATCH_BYTES of shared memory -- crossing rays on their
+    // way to the lane that walks them (16 bytes each, at most 32 KPT <= 128), then the source regions of the step
+    uint32_t *const qbuf = reinterpret_cast<uint32_t *>(scratch);
     const int warp = BLOCK ? (int)(threadIdx.x >> 5) : 0;
     const int n_warps = BLOCK ? (int)(blockDim.x >> 5) : 1;
     const int Z = w.Z;
@@ -253,8 +266,84 @@ __device__ __forceinline__ void walk_stack_warp(const WalkParams &w, const long 
                 z_after[r] = (k >= lo && k < hi) ? home : zh[r];
             }
         }
-        // Rays that cross a boundary: the general loop of solver.c:409-525, one code copy
-        while (__any_sync(0xffffffffu, crossing != 0)) {
+        // Rays that cross a boundary: the general loop of solver.c:409-525, one code copy.
+        // (One warp per stack only: with several warps per stack -- tall stacks -- the per-lane form measured
+        // 4 % faster, 2.5 against 2.6 ms on the small problem.)
+        constexpr bool COMPACT = MOC_WALK_COMPACT_CROSSING && !BLOCK;
+        // A quarter of the rays cross at a typical step, one to three per lane: walked where they live, the warp
+        // needs max-over-lanes passes with a third of its lanes busy.  Instead the crossing rays are numbered
+        // across the warp (one shuffle scan) and dealt out one per lane through shared memory: (height, ray,
+        // first slot, last slot) go out, (segments | exit, height, stencil bytes) come back.
+        if (COMPACT && __any_sync(0xffffffffu, crossing != 0)) {
+            const uint32_t mine = __popc(crossing);
+            const uint32_t incl = warp_inclusive_scan_u32(mine, lane);
+            const uint32_t n_cross = __shfl_sync(0xffffffffu, incl, 31);
+            {
+                uint32_t at = incl - mine;
+#pragma unroll
+                for (int r = 0; r < KPT; r++)
+                    if ((crossing >> r) & 1u)
+                        scratch[at++] = make_uint4(__float_as_uint(zh[r]), (uint32_t)(k0 + r), cursor[r], end[r]);
+            }
+            __syncwarp();
+            for (uint32_t x = lane; x < n_cross; x += 32) {
+                const uint4 ray = scratch[x];
+                const int k = (int)ray.y;
+                const float home = UP ? __fmul_rn(w.z_sep, (float)k) : __fmul_rn(w.z_sep, (float)(k + 1));
+                const uint32_t j0 = ray.z, j_end = ray.w;
+                float s = s_full, z_cur = __uint_as_float(ray.x);
+                int c = interval_of<UP, FAST>(w, z_cur);
+                uint32_t made = 0, pc = 0, left = 0;
+                bool finished = false;
+                do {
+                    bool out = false;
+                    // float z = z_height + s * cos(p_angle)   -- double product, double sum, narrowed
+                    float z = (float)__dadd_rn((double)z_cur, __dmul_rn((double)s, cos_p));
+                    float ds;
+                    if (interval_of<UP, FAST>(w, z) == c) {
+                        finished = true;
+                        ds = s;
+                    } else {
+                        c += UP ? 1 : -1;
+                        z = (float)__dmul_rn(w.fine_dz, (double)c);   // (float)c is exact, so is (double)(float)c
+                        ds = div_by_cos(__fsub_rn(z, z_cur), cos_p, rcos);
+                        s = __fsub_rn(s, ds);
+                        if (s <= 0.0f) finished = true;
+                        if (z <= 0.0f || z >= w.node_dz_f) {
+                            finished = true;
+                            out = true;
+                            left = 1u << 31;
+                        }
+                    }
+                    if (FILL) {
+                        const uint32_t slot = base + (j0 + made) * w.Zs + k;
+                        const bool store = j0 + made < j_end;
+                        const uint32_t byte = emit_geometry<FAST>(w, z_cur, ds, slot, store);
+                        if (made < 4) pc |= byte << (8 * made);
+                        else if (store) w.rec_code[slot] = byte << 24;   // fifth and later: parked in the record
+                    }
+                    made++;
+                    z_cur = (last || out) ? home : z;   // solver.c:514-523, after EVERY 3D segment
+                } while (!finished);
+                scratch[x] = make_uint4(made | left, __float_as_uint(z_cur), pc, 0u);
+            }
+            __syncwarp();
+            {
+                uint32_t at = incl - mine;
+#pragma unroll
+                for (int r = 0; r < KPT; r++)
+                    if ((crossing >> r) & 1u) {
+                        const uint4 res = scratch[at++];
+                        cnt[r] = res.x & 0x7fffffffu;
+                        exits |= (res.x >> 31) << r;
+                        z_after[r] = __uint_as_float(res.y);
+                        if (FILL) pcode[r] = res.z;
+                    }
+            }
+            __syncwarp();   // the scratch is reused (source regions below, the next step's rays)
+        }
+        // the per-lane form: every lane walks its own crossing rays, one after the other
+        while (!COMPACT && __any_sync(0xffffffffu, crossing != 0)) {
             if (crossing) {
                 const int r = __ffs(crossing) - 1;
                 crossing &= crossing - 1;
@@ -348,11 +437,28 @@ __device__ __forceinline__ void walk_stack_warp(const WalkParams &w, const long 
                 run_exits += (exits >> r) & 1u;
             }
         }
+        // what this warp really processed: its segments are draws serial_at + warp_first .. + warp_cnt - 1
+        uint32_t done_exits = __reduce_add_sync(0xffffffffu, taken_exits);
+        uint32_t done_cnt = __reduce_add_sync(0xffffffffu, taken_cnt);
         if (FILL) {
             // ---- the source region of every segment just written: rand() draw number `serial`
-            // (solver.c:476-483).  One code copy; a lane runs through its own rays' segments.
-            uint32_t todo = taken, m = 0, cnt_r = 0, cur = 0, pc = 0;
-            unsigned long long ser = 0;
+            // (solver.c:476-483).
+            // The draws of a step are consecutive, so the hash + remainder (two thirds of the work here) is
+            // dealt out evenly -- lane l takes draws l, l + 32, ... -- and parked in shared memory; the lanes
+            // then only pick up the regions of their own rays' segments (a lane's rays hold 1 to ~6 segments,
+            // walking them with the hash inside kept 13 lanes of 32 busy).
+            const uint32_t warp_cnt = done_cnt;
+            const uint32_t warp_first = __shfl_sync(0xffffffffu, cnt_before, 0);
+            const bool staged = (MOC_WALK_STAGED_HASH && !BLOCK) && warp_cnt <= WALK_SCRATCH_BYTES / 4;
+            if (staged) {
+                for (uint32_t t = lane; t < warp_cnt; t += 32) {
+                    const uint32_t draw = moc_rand31(w.seed, w.rand_base + serial_at + warp_first + t);
+                    qbuf[t] = w.mod_fast ? fastmod31(draw, w.n_regions, w.mod_magic, w.mod_shift) : draw % w.n_regions;
+                }
+                __syncwarp();
+            }
+            // One code copy; a lane runs through its own rays' segments.
+            uint32_t todo = taken, m = 0, cnt_r = 0, cur = 0, pc = 0, rel = 0;
             for (;;) {
                 if (m == cnt_r) {
                     if (!todo) break;
@@ -361,14 +467,18 @@ __device__ __forceinline__ void walk_stack_warp(const WalkParams &w, const long 
                     m = 0;
                     cnt_r = pick<KPT>(cnt, r);
                     pc = pick<KPT>(pcode, r);
-                    ser = serial_at + pick<KPT>(first_serial, r);
+                    rel = pick<KPT>(first_serial, r);
                     cur = base + pick<KPT>(cursor, r) * w.Zs + (k0 + r);
                 }
                 const uint32_t slot = cur + m * w.Zs;
                 const uint32_t byte = m < 4 ? ((pc >> (8 * m)) & 0xffu) : (w.rec_code[slot] >> 24);
-                const unsigned long long serial = ser + m;
-                const uint32_t draw = moc_rand31(w.seed, w.rand_base + serial);
-                const uint32_t qsr = w.mod_fast ? fastmod31(draw, w.n_regions, w.mod_magic, w.mod_shift) : draw % w.n_regions;
+                const unsigned long long serial = serial_at + rel + m;
+                uint32_t qsr;
+                if (staged) qsr = qbuf[rel - warp_first + m];
+                else {
+                    const uint32_t draw = moc_rand31(w.seed, w.rand_base + serial);
+                    qsr = w.mod_fast ? fastmod31(draw, w.n_regions, w.mod_magic, w.mod_shift) : draw % w.n_regions;
+                }
                 w.rec_code[slot] = qsr | (byte << 24);
                 if (w.digest) {
                     const unsigned long long row = (unsigned long long)qsr * w.fai + (byte & 63u) + (byte >> 6);
@@ -379,6 +489,7 @@ __device__ __forceinline__ void walk_stack_warp(const WalkParams &w, const long 
                 }
                 m++;
             }
+            if (staged) __syncwarp();   // every lane has read its regions before the scratch is written again
         }
 #pragma unroll
         for (int r = 0; r < KPT; r++) {
@@ -388,8 +499,6 @@ __device__ __forceinline__ void walk_stack_warp(const WalkParams &w, const long 
                 else made_total[r] += cnt[r];
             }
         }
-        uint32_t done_exits = __reduce_add_sync(0xffffffffu, taken_exits);
-        uint32_t done_cnt = __reduce_add_sync(0xffffffffu, taken_cnt);
         if (BLOCK) {
             // second exchange: what the warps really processed (the first one's slots are still being read)
             if (lane == 0) xw[33 + warp] = ((unsigned long long)done_exits << 32) | done_cnt;
@@ -471,6 +580,7 @@ __device__ __forceinline__ void walk_stack_warp(const WalkParams &w, const long 
 template <int KPT, bool FILL, bool UP, bool FAST>
 __global__ void __launch_bounds__(128) stack_walk_warp_kernel(const WalkParams w, long long dir_before, long long n_dir)
 {
+    __shared__ uint4 scratch[4][WALK_SCRATCH_BYTES / 16];
     const int lane = threadIdx.x & 31;
     const int H = w.P / 2, per_track = UP ? H : w.P - H;
     const long long step = (long long)gridDim.x * (blockDim.x >> 5);
@@ -479,7 +589,7 @@ __global__ void __launch_bounds__(128) stack_walk_warp_kernel(const WalkParams w
         const long long i = target / per_track;
         const int j = (int)(target - i * per_track) + (UP ? 0 : H);
         const long long pair = i * w.P + j;
-        walk_stack_warp<KPT, FILL, UP, FAST, false>(w, pair, pair - w.first_pair, i, j, lane);
+        walk_stack_warp<KPT, FILL, UP, FAST, false>(w, pair, pair - w.first_pair, i, j, lane, scratch[threadIdx.x >> 5]);
     }
 }
 
@@ -495,7 +605,7 @@ __global__ void __launch_bounds__(512) stack_walk_block_kernel(const WalkParams 
         const long long i = target / per_track;
         const int j = (int)(target - i * per_track) + (UP ? 0 : H);
         const long long pair = i * w.P + j;
-        walk_stack_warp<4, FILL, UP, FAST, true>(w, pair, pair - w.first_pair, i, j, lane, xw);
+        walk_stack_warp<4, FILL, UP, FAST, true>(w, pair, pair - w.first_pair, i, j, lane, nullptr, xw);
         __syncthreads();   // xw is reused by the next stack
     }
 }
