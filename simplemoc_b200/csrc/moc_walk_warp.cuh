@@ -7,13 +7,17 @@
  *
  *   - the per-step prefix over the stack (exits below a ray, segments below a ray) is ONE 32-bit
  *     warp shuffle scan of a packed (exits | segments) word, the step totals are two REDUX
- *     instructions; the one-warp form needs no shared memory and no __syncthreads, the
- *     several-warp form passes the warps' totals through 66 words of shared memory;
+ *     instructions; the one-warp form needs no __syncthreads (2 KB of shared memory per warp carry
+ *     the crossing rays and the step's source regions between lanes, see below), the several-warp
+ *     form passes the warps' totals through 66 words of shared memory;
  *   - one launch per ray direction (upward / downward), the direction is a template parameter:
  *     no per-ray direction branches and only one instantiation resident in the instruction caches;
  *   - rays that stay inside their fine axial interval for the whole 2D segment are handled
  *     branch-free, unrolled over the lane's rays; the interval-crossing walk exists ONCE, in a loop
- *     the lanes enter only for the rays that need it;
+ *     the lanes enter only for the rays that need it -- in the one-warp form the crossing rays of a
+ *     step (a quarter of the stack) are first numbered across the warp and dealt out one per lane
+ *     (COMPACT), and the hash + remainder of the step's consecutive rand() draws is spread evenly
+ *     over the lanes the same way (staged): both loops ran with 10-13 lanes of 32 busy before;
  *   - fine intervals are computed without the IEEE-division sequence and without conversion
  *     instructions (XU pipe): a Newton quotient on FMA units and a directed-rounding add, used
  *     only after interval_check_kernel verified it against the division for every float of the
