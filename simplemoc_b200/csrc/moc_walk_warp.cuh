@@ -461,14 +461,39 @@ __device__ __forceinline__ void walk_stack_warp(const WalkParams &w, const long 
                 }
                 __syncwarp();
             }
+            auto tally_digest = [&](uint32_t qsr, uint32_t byte, unsigned long long serial) {
+                const unsigned long long row = (unsigned long long)qsr * w.fai + (byte & 63u) + (byte >> 6);
+                dg[0] += 1ull;
+                dg[1] += row;
+                dg[2] += (row + 1ull) * (2ull * serial + 1ull);
+                dg[3] ^= mix64(serial * 0x100000001B3ULL + row);
+            };
+            // Staged: the first segment of every ray (for three rays in four the only one) is finished
+            // branch-free, unrolled over the lane's rays; the loop below is left with the further segments of
+            // the rays that crossed.  Otherwise the loop takes every segment.
+            uint32_t todo = taken;
+            const uint32_t m0 = staged ? 1u : 0u;
+            if (staged) {
+                todo = 0;
+#pragma unroll
+                for (int r = 0; r < KPT; r++) {
+                    if ((taken >> r) & 1u) {
+                        const uint32_t byte = pcode[r] & 0xffu;
+                        const uint32_t qsr = qbuf[first_serial[r] - warp_first];
+                        w.rec_code[base + cursor[r] * w.Zs + (k0 + r)] = qsr | (byte << 24);
+                        if (w.digest) tally_digest(qsr, byte, serial_at + first_serial[r]);
+                        todo |= cnt[r] > 1u ? (1u << r) : 0u;
+                    }
+                }
+            }
             // One code copy; a lane runs through its own rays' segments.
-            uint32_t todo = taken, m = 0, cnt_r = 0, cur = 0, pc = 0, rel = 0;
+            uint32_t m = 0, cnt_r = 0, cur = 0, pc = 0, rel = 0;
             for (;;) {
                 if (m == cnt_r) {
                     if (!todo) break;
                     const int r = __ffs(todo) - 1;
                     todo &= todo - 1;
-                    m = 0;
+                    m = m0;
                     cnt_r = pick<KPT>(cnt, r);
                     pc = pick<KPT>(pcode, r);
                     rel = pick<KPT>(first_serial, r);
@@ -484,13 +509,7 @@ __device__ __forceinline__ void walk_stack_warp(const WalkParams &w, const long 
                     qsr = w.mod_fast ? fastmod31(draw, w.n_regions, w.mod_magic, w.mod_shift) : draw % w.n_regions;
                 }
                 w.rec_code[slot] = qsr | (byte << 24);
-                if (w.digest) {
-                    const unsigned long long row = (unsigned long long)qsr * w.fai + (byte & 63u) + (byte >> 6);
-                    dg[0] += 1ull;
-                    dg[1] += row;
-                    dg[2] += (row + 1ull) * (2ull * serial + 1ull);
-                    dg[3] ^= mix64(serial * 0x100000001B3ULL + row);
-                }
+                if (w.digest) tally_digest(qsr, byte, serial);
                 m++;
             }
             if (staged) __syncwarp();   // every lane has read its regions before the scratch is written again
