@@ -1,0 +1,97 @@
+"""The lane-spread pairwise_sum of update_sources_coop_kernel (simplemoc_b200/csrc/moc_kernels.cuh: tree_slot,
+tree_combine, tree_depth) performs the additions of the reference's recursion (src/utils.c:29-45) in the
+reference's order -- checked SYMBOLICALLY for every group count the kernel accepts (1 <= G <= 512), not only for
+the seven the GPU parity test runs (tests/test_gpu_parity.py::test_reductions_bit_exact_on_identical_flux).
+
+This file restates the index arithmetic of those three device functions line by line in Python and compares
+expression trees; it does not run the kernel (the GPU tests do) and imports nothing from oracle/."""
+import os
+import re
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+KERNELS = os.path.join(os.path.dirname(HERE), "simplemoc_b200", "csrc", "moc_kernels.cuh")
+
+
+def reference_tree(lo, n):
+    """utils.c:29-45 as an expression tree: a leaf of <= 16 terms is summed left to right from 0."""
+    if n <= 16:
+        return ("seq", lo, n)
+    half = n // 2
+    return ("add", reference_tree(lo, half), reference_tree(lo + half, n - half))
+
+
+def tree_depth(n):
+    d = 0
+    while n > 16:
+        n -= n // 2
+        d += 1
+    return d
+
+
+def tree_slot(n, depth, sub):
+    lo, sz, split_mask, level = 0, n, 0, 0
+    while level < depth:
+        if sz <= 16:
+            break
+        split_mask |= 1 << level
+        half = sz // 2
+        if (sub >> (depth - 1 - level)) & 1:
+            lo += half
+            sz -= half
+        else:
+            sz = half
+        level += 1
+    owner = (sub & ((1 << (depth - level)) - 1)) == 0
+    return lo, sz, owner, split_mask
+
+
+def lane_spread_tree(n):
+    """What lane 0 of a 2^depth-lane group holds after tree_combine, as an expression tree."""
+    depth = tree_depth(n)
+    lanes = 1 << depth
+    slots = [tree_slot(n, depth, sub) for sub in range(lanes)]
+    # a lane that owns no leaf carries the 0.f it was initialised with: it must never be added
+    v = [("seq", lo, sz) if owner else None for lo, sz, owner, _ in slots]
+    for level in range(depth - 1, -1, -1):
+        span = 1 << (depth - level)
+        right = [v[sub + span // 2] if (sub % span) + span // 2 < span and sub + span // 2 < lanes else None
+                 for sub in range(lanes)]            # __shfl_down_sync(v, span / 2, width = 2^depth)
+        for sub in range(lanes):
+            if sub & (span - 1) == 0 and (slots[sub][3] >> level) & 1:
+                assert v[sub] is not None and right[sub] is not None, (n, level, sub)
+                v[sub] = ("add", v[sub], right[sub])
+    return v[0]
+
+
+@pytest.mark.parametrize("lo,hi", [(1, 129), (129, 257), (257, 385), (385, 513)])
+def test_lane_spread_tree_is_the_reference_recursion(lo, hi):
+    for n in range(lo, hi):
+        assert tree_depth(n) <= 5                      # the kernel's precondition (G <= 512)
+        assert lane_spread_tree(n) == reference_tree(0, n), n
+
+
+def test_every_term_is_summed_exactly_once():
+    for n in (1, 16, 17, 33, 104, 130, 200, 511, 512):
+        depth = tree_depth(n)
+        covered = []
+        for sub in range(1 << depth):
+            lo, sz, owner, _ = tree_slot(n, depth, sub)
+            assert sz <= 16
+            if owner:
+                covered += list(range(lo, lo + sz))
+        assert sorted(covered) == list(range(n)), n
+
+
+def test_the_model_follows_the_device_code():
+    """Guard against the kernel and this restatement drifting apart: the lines the model mirrors are still there."""
+    src = open(KERNELS).read()
+    for needle in (r"if \(t\.sz <= 16\) break;",
+                   r"t\.split_mask \|= 1u << level;",
+                   r"if \(\(sub >> \(depth - 1 - level\)\) & 1\) \{ t\.lo \+= half; t\.sz -= half; \}",
+                   r"t\.owner = \(sub & \(\(1 << \(depth - level\)\) - 1\)\) == 0;",
+                   r"__shfl_down_sync\(0xffffffffu, v, span / 2, 1 << depth\)",
+                   r"if \(\(sub & \(span - 1\)\) == 0 && \(\(t\.split_mask >> level\) & 1u\)\) v = __fadd_rn\(v, right\);",
+                   r"while \(n > 16\) \{ n -= n / 2; d\+\+; \}"):
+        assert re.search(needle, src), needle
