@@ -1,9 +1,11 @@
-"""The lane-spread pairwise_sum of update_sources_coop_kernel (simplemoc_b200/csrc/moc_kernels.cuh: tree_slot,
-tree_combine, tree_depth) performs the additions of the reference's recursion (src/utils.c:29-45) in the
-reference's order -- checked SYMBOLICALLY for every group count the kernel accepts (1 <= G <= 512), not only for
-the seven the GPU parity test runs (tests/test_gpu_parity.py::test_reductions_bit_exact_on_identical_flux).
+"""The two parallel forms of the reference's pairwise_sum (src/utils.c:29-45) in simplemoc_b200/csrc/moc_kernels.cuh
+-- the lane-spread sums of update_sources_coop_kernel (tree_slot, tree_combine, tree_depth) and the 256-thread
+pairwise_sum_cta of the K2-K4 reductions -- perform the recursion's additions in the recursion's order: checked
+SYMBOLICALLY for every group count the kernel accepts (1 <= G <= 512) and for region counts 1..1200 plus the
+BASELINE configurations', not only for the sizes the GPU parity tests run
+(tests/test_gpu_parity.py::test_reductions_bit_exact_on_identical_flux).
 
-This file restates the index arithmetic of those three device functions line by line in Python and compares
+This file restates the index arithmetic of those device functions line by line in Python and compares
 expression trees; it does not run the kernel (the GPU tests do) and imports nothing from oracle/."""
 import os
 import re
@@ -84,6 +86,54 @@ def test_every_term_is_summed_exactly_once():
         assert sorted(covered) == list(range(n)), n
 
 
+def cta_tree(n):
+    """pairwise_sum_cta (256 threads, the top 8 levels of the recursion spread over threads): what slots[0]
+    holds at the end.  A thread's own subtree is summed by the device recursion `pairwise_sum`, which is the
+    reference's (same split, same 16-term base case)."""
+    D = 8
+    slots = [None] * 256
+    for t in range(256):
+        lo, sz, depth = 0, n, 0
+        while depth < D:
+            if sz <= 16:
+                break
+            half = sz // 2
+            if (t >> (D - 1 - depth)) & 1:
+                lo += half
+                sz -= half
+            else:
+                sz = half
+            depth += 1
+        if t & ((1 << (D - depth)) - 1) == 0:
+            slots[t] = reference_tree(lo, sz)
+    for level in range(D - 1, -1, -1):
+        span = 1 << (D - level)
+        new = list(slots)
+        for t in range(0, 256, span):
+            s2, split_all_the_way = n, True
+            for d in range(level):
+                if s2 <= 16:
+                    split_all_the_way = False
+                    break
+                half = s2 // 2
+                s2 = s2 - half if (t >> (D - 1 - d)) & 1 else half
+            if split_all_the_way and s2 > 16:
+                assert slots[t] is not None and slots[t + span // 2] is not None, (n, level, t)
+                new[t] = ("add", slots[t], slots[t + span // 2])
+        slots = new
+    return slots[0]
+
+
+def test_cta_tree_is_the_reference_recursion():
+    """Region counts of every configuration in BASELINE.json (2 250, 6 750, 15 000, 67 500), every n up to 1 200,
+    and sizes around the powers of two where subtrees become leaves."""
+    sizes = set(range(1, 1201)) | {2250, 6750, 15000, 67500, 100003}
+    for k in range(4, 17):
+        sizes |= {(1 << k) - 1, 1 << k, (1 << k) + 1, 17 << (k - 4), (17 << (k - 4)) - 1}
+    for n in sorted(sizes):
+        assert cta_tree(n) == reference_tree(0, n), n
+
+
 def test_the_model_follows_the_device_code():
     """Guard against the kernel and this restatement drifting apart: the lines the model mirrors are still there."""
     src = open(KERNELS).read()
@@ -93,5 +143,9 @@ def test_the_model_follows_the_device_code():
                    r"t\.owner = \(sub & \(\(1 << \(depth - level\)\) - 1\)\) == 0;",
                    r"__shfl_down_sync\(0xffffffffu, v, span / 2, 1 << depth\)",
                    r"if \(\(sub & \(span - 1\)\) == 0 && \(\(t\.split_mask >> level\) & 1u\)\) v = __fadd_rn\(v, right\);",
-                   r"while \(n > 16\) \{ n -= n / 2; d\+\+; \}"):
+                   r"while \(n > 16\) \{ n -= n / 2; d\+\+; \}",
+                   r"if \(\(t >> \(D - 1 - depth\)\) & 1\) \{ lo \+= half; sz -= half; \}",
+                   r"if \(\(t & \(\(1 << \(D - depth\)\) - 1\)\) == 0\) \{",
+                   r"s2 = \(\(t >> \(D - 1 - d\)\) & 1\) \? s2 - half : half;",
+                   r"if \(split_all_the_way && s2 > 16\) slots\[t\] = __fadd_rn\(slots\[t\], slots\[t \+ span / 2\]\);"):
         assert re.search(needle, src), needle
