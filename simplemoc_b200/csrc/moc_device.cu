@@ -519,6 +519,13 @@ static int create_common(const Input *I, const Params *P, int device, int source
         moc_set_error("axial_exp=2 needs fai >= 3 (the edge stencil of solver.c:55-112 reads three rows)");
         return MOC_EINVAL;
     }
+    if (I->fai < 2) {
+        // the ray trace takes `fine interval % fai` with a 32-bit reciprocal, floor(2^32 / fai) + 1, which does not
+        // exist for fai = 1 (tests/test_tree_model.py); a flat source over a single fine interval is refused
+        // rather than tallied into the wrong rows
+        moc_set_error("unsupported size: fai=%d (min 2)", I->fai);
+        return MOC_EINVAL;
+    }
     if (I->fai > 63 || I->n_source_regions_per_node >= (1 << 24) || I->z_stacked > 16384) {
         moc_set_error("unsupported size: fai=%d (max 63), N=%ld (max 2^24-1), z_stacked=%d (max 16384)",
                       I->fai, I->n_source_regions_per_node, I->z_stacked);

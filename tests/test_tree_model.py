@@ -149,3 +149,26 @@ def test_the_model_follows_the_device_code():
                    r"s2 = \(\(t >> \(D - 1 - d\)\) & 1\) \? s2 - half : half;",
                    r"if \(split_all_the_way && s2 > 16\) slots\[t\] = __fadd_rn\(slots\[t\], slots\[t \+ span / 2\]\);"):
         assert re.search(needle, src), needle
+
+
+def test_fai_magic_remainder_is_exact():
+    """emit_geometry (moc_walk_warp.cuh) takes `iq % fai` as iq - umulhi(iq, floor(2^32 / fai) + 1) * fai whenever
+    iq < 2^20, with the reciprocal held in 32 bits (moc_sweep.inl), and moc_create accepts 2 <= fai <= 63:
+    exhaustive over that whole range.  fai = 1 has no 32-bit reciprocal (2^32 + 1 wraps to 1) -- refused."""
+    import numpy as np
+    csrc = os.path.dirname(KERNELS)
+    assert "(unsigned)iq < (1u << 20) ? iq - (int)__umulhi((uint32_t)iq, w.fai_magic) * w.fai : iq % w.fai" in \
+        open(os.path.join(csrc, "moc_walk_warp.cuh")).read()
+    assert "w.fai_magic = (unsigned int)((1ull << 32) / (unsigned long long)std::max(h->F, 1)) + 1u;" in \
+        open(os.path.join(csrc, "moc_sweep.inl")).read()
+    create = open(os.path.join(csrc, "moc_device.cu")).read()
+    assert "if (I->fai < 2) {" in create and "if (I->fai > 63 ||" in create
+    iq = np.arange(1 << 20, dtype=np.uint64)
+
+    def remainder(fai):
+        magic = np.uint64(((1 << 32) // fai + 1) & 0xFFFFFFFF)      # (unsigned int)(...) + 1u
+        return iq - ((iq * magic) >> np.uint64(32)) * np.uint64(fai)
+
+    for fai in range(2, 64):
+        assert np.array_equal(remainder(fai), iq % np.uint64(fai)), fai
+    assert not np.array_equal(remainder(1), iq % np.uint64(1))      # why fai = 1 is refused
