@@ -78,6 +78,10 @@ CASES = {
     "polar2": [3, 3, 2, 3, 2, 2.0, 8.0, 8, 2, 12, 0, 1, 10, 21.42, 400.0, 0.01, 200, 0],
     "onecell": [3, 3, 1, 3, 2, 2.0, 4.0, 8, 4, 16, 0, 1, 10, 21.42, 400.0, 0.01, 200, 0],
     "zone": [3, 3, 4, 3, 2, 2.0, 400.0, 8, 4, 16, 0, 1, 10, 21.42, 400.0, 0.01, 200, 0],
+    # flat source over one and over two fine intervals per coarse one: legal in the reference, fai < 3.  CPU only so
+    # far (oracle against the reference + digests); moc_create refuses fai = 1 (DESIGN "Size limits")
+    "flat_f1": [3, 3, 4, 1, 0, 2.0, 4.0, 8, 4, 16, 0, 1, 10, 21.42, 400.0, 0.01, 200, 0],
+    "flat_f2": [3, 3, 4, 2, 0, 2.0, 4.0, 8, 4, 16, 0, 1, 10, 21.42, 400.0, 0.01, 200, 0],
     # group counts whose pairwise_sum trees are uneven (utils.c:29-45: 33 = 16 + 17 -> 17 = 8 + 9;
     # 130 = 65 + 65 -> 32 + 33 -> ...; 200): the reductions spread those trees over lanes
     "g33": [3, 3, 3, 4, 2, 2.5, 8.0, 6, 2, 33, 0, 1, 6, 21.42, 400.0, 0.01, 96, 0],
