@@ -202,3 +202,29 @@ def test_exchange_plan_follows_comms_c(built):
     # a problem too small for a single message exchanges nothing
     tiny = m.derive(m.input_from_values(CASES["tiny"]))
     assert exchange_plan(tiny, grid) == []
+
+
+def test_build_tracks_matches_the_oracle_on_random_configurations(built):
+    """The digests above pin moc_build_tracks on the named cases; here the same arrays are compared with the
+    oracle's construction (itself bit-identical to the reference's on these very configurations:
+    tests/test_oracle_vs_ref.py) for 80 random inputs -- 1-6 coarse / fine axial intervals, flat and quadratic
+    source, odd group counts, decomposed nodes."""
+    from oracle_lib import OracleCase
+    from test_oracle_vs_ref import _random_configurations
+    checked = 0
+    for vals, seed in _random_configurations(80, 20261017):
+        host = m.HostProblem(m.derive(m.input_from_values(vals)), seed=seed)
+        o = OracleCase(vals, seed=seed)
+        if o.n_segments.min() >= 0:     # negative draws: the library clamps what the reference leaves undefined
+            what = f"vals={vals} seed={seed}"
+            assert host.rand_calls == o.init_rand_calls, what
+            for name, mine, theirs in (("az_weight", api.HOST_AZ_WEIGHT, o.az_weight), ("n_segments", api.HOST_N_SEGMENTS, o.n_segments),
+                                       ("seg_lengths", api.HOST_SEG_LENGTHS, o.seg_lengths), ("p_weight", api.ARR_P_WEIGHT, o.p_weight),
+                                       ("z_height", api.ARR_Z_HEIGHT, o.z_height), ("xs", api.HOST_XS, o.xs),
+                                       ("scatter", api.HOST_SCATTER, o.scatter), ("fine_source", api.ARR_FINE_SOURCE, o.fine_source),
+                                       ("sigT", api.ARR_SIGT, o.sigT), ("xs_index", api.HOST_XS_INDEX, o.xs_index),
+                                       ("vol", api.HOST_VOL, o.vol)):
+                assert np.array_equal(np.asarray(host.get(mine)).ravel(), np.asarray(theirs).ravel()), f"{name}: {what}"
+            checked += 1
+        host.close(); o.close()
+    assert checked >= 60
