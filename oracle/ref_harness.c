@@ -14,6 +14,11 @@
  *                             ref_expf_override.c                (exact-exp oracle)
  *   libsimplemoc_ref_omp.so   stock Makefile flags, OpenMP, libc rand_r
  *                             (timing baseline only; its keff is NaN)
+ *   libsimplemoc_ref_mpi.so   as the first, every source compiled with -DMPI against the
+ *                             in-process MPI of oracle/mpi_stub (ranks = pthreads): the pin of
+ *                             comms.c:5-196, init.c:162-225 and the MPI reductions of solver.c
+ *   libsimplemoc_ref_ofast.so as the first with -Ofast -ffast-math -mfma: reference-vs-reference
+ *                             noise floor (tools/tolerance_anchor.py)
  */
 #include "SimpleMOC_header.h"
 #include <fcntl.h>
@@ -99,7 +104,11 @@ RefCase *ref_case_create_tracks(const char *input_file, int small, uint64_t seed
     omp_set_num_threads(c->I.nthreads);
 #endif
     c->P = build_tracks(&c->I);
-    c->grid = init_mpi_grid(c->I);
+#ifndef MPI
+    c->grid = init_mpi_grid(c->I);   /* without MPI: returns an unset grid (init.c:166) */
+#else
+    memset(&c->grid, 0, sizeof c->grid);   /* collective under MPI: ref_mpi_run(..., what & 1) or ref_mpi_set_grid */
+#endif
     c->n_xs_regions = c->I.n_source_regions_per_node / 8;
     long tot = 0;
     for (long i = 0; i < c->I.ntracks_2D; i++) tot += c->P.tracks_2D[i].n_segments;
@@ -253,6 +262,69 @@ void ref_copy_source_meta(RefCase *c, int *xs_index, float *vol)
         vol[i] = c->P.sources[i].vol;
     }
 }
+
+#ifdef MPI
+/* ---- the communication path (src/main.c:66-71, 73-91 under -DMPI), one pthread per rank ----
+ * cases[r] is rank r's domain, built on the calling thread with mpi_stub_set_rank(r) (see
+ * ref_mpi_case_create).  what: 1 = init_mpi_grid (init.c:162-225; dims {2,2,1}: four ranks),
+ * 2 = fast_transfer_boundary_fluxes (comms.c:5-196), 4 = renormalize_flux, 8 = compute_keff
+ * (keff_out[r]; only rank 0's is defined, solver.c:1394-1425).  Without bit 1 the grids the cases
+ * already hold are used (ref_mpi_set_grid: a 1x1x1 or any other neighbour table). */
+typedef struct { RefCase **cases; int what; float *keff_out; } MpiJob;
+
+static void mpi_rank_main(int rank, void *arg)
+{
+    MpiJob *job = (MpiJob *)arg;
+    RefCase *c = job->cases[rank];
+    if (job->what & 1) c->grid = init_mpi_grid(c->I);
+    if (job->what & 2) fast_transfer_boundary_fluxes(c->P, c->I, c->grid);
+    if (job->what & 4) renormalize_flux(c->P, c->I, c->grid);
+    if (job->what & 8) job->keff_out[rank] = compute_keff(c->P, c->I, c->grid);
+}
+
+int ref_mpi_run(int nranks, RefCase **cases, int what, float *keff_out)
+{
+    MpiJob job = { cases, what, keff_out };
+    int saved = quiet_begin();
+    int rc = mpi_stub_run(nranks, mpi_rank_main, &job);
+    quiet_end(saved);
+    return rc;
+}
+
+/* rank `rank` of `nranks`: calculate_derived_inputs asks MPI_Comm_rank (init.c:7-11) */
+RefCase *ref_mpi_case_create(const char *input_file, uint64_t seed, int rank, int nranks)
+{
+    mpi_stub_world(nranks);
+    mpi_stub_set_rank(rank);
+    RefCase *c = ref_case_create_tracks(input_file, 0, seed, 1, 0, NULL);
+    mpi_stub_set_rank(0);
+    return c;
+}
+
+/* the twelve neighbour ranks in CommGrid order (x_pos_src .. z_neg_dest) */
+void ref_mpi_get_grid(RefCase *c, int out[12])
+{
+    const int v[12] = { c->grid.x_pos_src, c->grid.x_pos_dest, c->grid.x_neg_src, c->grid.x_neg_dest,
+                        c->grid.y_pos_src, c->grid.y_pos_dest, c->grid.y_neg_src, c->grid.y_neg_dest,
+                        c->grid.z_pos_src, c->grid.z_pos_dest, c->grid.z_neg_src, c->grid.z_neg_dest };
+    memcpy(out, v, sizeof v);
+}
+void ref_mpi_set_grid(RefCase *c, const int in[12])
+{
+    c->grid.cart_comm_3d = 0;
+    MPI_Type_contiguous(c->I.n_egroups, MPI_FLOAT, &c->grid.Flux_Array);   /* init.c:215-219 */
+    c->grid.x_pos_src = in[0]; c->grid.x_pos_dest = in[1]; c->grid.x_neg_src = in[2]; c->grid.x_neg_dest = in[3];
+    c->grid.y_pos_src = in[4]; c->grid.y_pos_dest = in[5]; c->grid.y_neg_src = in[6]; c->grid.y_neg_dest = in[7];
+    c->grid.z_pos_src = in[8]; c->grid.z_pos_dest = in[9]; c->grid.z_neg_src = in[10]; c->grid.z_neg_dest = in[11];
+}
+/* the random stream is process-global in the reference: continue case c's stream where it stood */
+void ref_mpi_select_stream(uint64_t seed, uint64_t calls)
+{
+    void ref_shim_set_calls(uint64_t c);
+    ref_shim_reset(seed);
+    ref_shim_set_calls(calls);
+}
+#endif
 
 /* the host-side Params/Input themselves, for driving the drop-in C-ABI of the
  * product with the reference's own (pointer-rich) structures */

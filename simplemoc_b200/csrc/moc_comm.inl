@@ -87,10 +87,17 @@ extern "C" int moc_comm_init(moc_handle *h, int nranks, int rank, const char id_
     CUDA_TRY(cudaSetDevice(h->device));
     nccl_unique_id id;
     memcpy(id.internal, id_in, 128);
+    comm_release(h);   // a second moc_comm_init replaces the communicator
     NCCL_TRY(g_nccl.comm_init_rank(&h->nccl_comm, nranks, id, rank));
     h->nranks = nranks;
     h->rank = rank;
     return MOC_OK;
+}
+
+static void comm_release(moc_handle *h)
+{
+    if (h->nccl_comm && g_nccl.comm_destroy) g_nccl.comm_destroy(h->nccl_comm);
+    h->nccl_comm = nullptr;
 }
 
 static int allreduce_scalars(moc_handle *h, float *dev, int count)

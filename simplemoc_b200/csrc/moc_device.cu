@@ -413,6 +413,12 @@ static int upload_static(moc_handle *h, const Params *P, const HostLayout &L, bo
 }
 
 static WalkParams walk_params(const moc_handle *h);
+// lane mapping of the attenuation kernel for G groups (moc_sweep.inl)
+struct LaneMap {
+    int L, NV4, NS;
+};
+static LaneMap choose_lanes(int G, int lanes_override);
+static void comm_release(moc_handle *h);   // moc_comm.inl: ncclCommDestroy
 
 // May the ray trace compute fine intervals with the FMA quotient (moc_walk_warp.cuh)?  Only if it
 // returns the integer of the IEEE division for every float a ray height can take: checked
@@ -485,6 +491,7 @@ extern "C" int moc_destroy(moc_handle *h)
     if (!h) return MOC_OK;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    comm_release(h);
     free_buffers(h->d);
     for (auto &e : h->ev)
         if (e) cudaEventDestroy(e);
@@ -519,11 +526,8 @@ static int create_common(const Input *I, const Params *P, int device, int source
         moc_set_error("axial_exp=2 needs fai >= 3 (the edge stencil of solver.c:55-112 reads three rows)");
         return MOC_EINVAL;
     }
-    if (I->fai < 2) {
-        // the ray trace takes `fine interval % fai` with a 32-bit reciprocal, floor(2^32 / fai) + 1, which does not
-        // exist for fai = 1 (tests/test_tree_model.py); a flat source over a single fine interval is refused
-        // rather than tallied into the wrong rows
-        moc_set_error("unsupported size: fai=%d (min 2)", I->fai);
+    if (I->fai < 1) {
+        moc_set_error("unsupported size: fai=%d (min 1)", I->fai);
         return MOC_EINVAL;
     }
     if (I->fai > 63 || I->n_source_regions_per_node >= (1 << 24) || I->z_stacked > 16384) {
@@ -539,6 +543,23 @@ static int create_common(const Input *I, const Params *P, int device, int source
                                  (double)((I->n_egroups + 31) / 32 * 32) >= 4294967296.0) {
         moc_set_error("fit-coefficient slab has more than 2^32 elements (the attenuation kernel indexes it with 32 bits)");
         return MOC_EINVAL;
+    }
+    {
+        // what every sweep would otherwise only find out after both ray-trace passes: a lane mapping for G ...
+        const LaneMap lm = choose_lanes(I->n_egroups, 0);
+        if (I->n_egroups < 1 || 4 * lm.L * lm.NV4 + lm.L * lm.NS < I->n_egroups || lm.NS > 16) {
+            moc_set_error("unsupported size: n_egroups=%d (1 .. 512: the attenuation kernel keeps a track's angular flux in "
+                          "the registers of at most 32 lanes x 16 groups)", I->n_egroups);
+            return MOC_EINVAL;
+        }
+        // ... and an exponential table that fits the shared memory of an SM (utils.c:55: N = 10 sqrt(1 / (0.08 precision));
+        // the default precision 0.01 gives 353 cells = 2.8 KB; 227 KB hold 29 055 cells, i.e. precision >= 1.5e-6)
+        if (P->expTable.N < 1 || sizeof(float) * 2 * ((size_t)P->expTable.N + 1) > 227 * 1024) {
+            moc_set_error("unsupported size: exponential table of %d cells (Input.precision %g): at most %d cells fit the "
+                          "227 KB of shared memory the attenuation kernel can keep it in", P->expTable.N, (double)I->precision,
+                          (int)(227 * 1024 / 8 - 1));
+            return MOC_EINVAL;
+        }
     }
     if (!synthetic && (rc = inspect_layout(I, P, source_stride, L))) return rc;
     CUDA_TRY(cudaSetDevice(device));

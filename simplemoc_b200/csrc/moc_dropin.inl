@@ -7,6 +7,7 @@ struct Mirror {
     bool dirty_sweep = false;   // device holds newer psi/z/flux than the host
     bool dirty_all = false;     // device holds newer everything
     std::vector<void *> registered;   // host slabs this library page-locked (cudaHostRegister)
+    const void *host_tracks = nullptr, *host_psi = nullptr, *host_src = nullptr;   // the slabs the mirror was built from
     bool exchanged = false;           // the last transport_sweep already ran the boundary exchange
 };
 static std::mutex g_mirror_mutex;
@@ -89,6 +90,19 @@ static Mirror &mirror_for(const Params *P, const Input *I, HostLayout &L, bool n
     std::lock_guard<std::mutex> lock(g_mirror_mutex);
     Mirror &m = g_mirrors[(const void *)P->tracks];
     bool created = false;
+    if (m.h) {
+        // Mirrors are keyed by the address of Params.tracks: a caller that frees its problem and builds another one
+        // may get the same address back from malloc.  A mirror whose sizes or slabs are not the incoming ones is stale.
+        if (inspect_layout(I, P, m.h->source_stride, L)) die(where);
+        const moc_handle *h = m.h;
+        if (h->T2 != I->ntracks_2D || h->T3 != I->ntracks || h->N != I->n_source_regions_per_node || h->P != I->n_polar_angles ||
+            h->Z != I->z_stacked || h->G != I->n_egroups || h->F != I->fai || h->I.axial_exp != I->axial_exp ||
+            m.host_tracks != (const void *)L.tracks || m.host_psi != (const void *)L.psi || m.host_src != (const void *)L.src) {
+            moc_destroy(m.h);
+            for (void *p : m.registered) cudaHostUnregister(p);
+            m = Mirror();
+        }
+    }
     if (!m.h) {
         int device = 0;
         cudaGetDevice(&device);
@@ -111,14 +125,26 @@ static Mirror &mirror_for(const Params *P, const Input *I, HostLayout &L, bool n
             }
         }
         created = true;
-    } else if (inspect_layout(I, P, m.h->source_stride, L)) {
-        die(where);
+        m.host_tracks = L.tracks;
+        m.host_psi = L.psi;
+        m.host_src = L.src;
     }
     if (created) pin_host_slabs(m, L);
     if (created || !g_resident) {
         // caller_streams: the non-resident transport_sweep moves the mutable state itself, chunk by
         // chunk, overlapped with the kernels (sweep_core); nothing to upload here
-        if (!(caller_streams && !g_resident) && upload_mutable(m.h, L, created || need_backward_psi)) die(where);
+        if (!(caller_streams && !g_resident)) {
+            if (upload_mutable(m.h, L, created || need_backward_psi)) die(where);
+        } else if (created) {
+            // the streamed sweep moves forward rows only: a new mirror still needs the backward rows once (they are
+            // scaled by renormalize_flux and moved by the exchange if the caller later switches to resident mode)
+            const size_t T3 = (size_t)m.h->T3, G = (size_t)m.h->G;
+            if (cudaMemcpy2DAsync(m.h->d.psi + G, sizeof(float) * 2 * G, L.psi + G, sizeof(float) * 2 * G, sizeof(float) * G,
+                                  T3, cudaMemcpyHostToDevice, m.h->stream) != cudaSuccess) {
+                moc_set_error("upload of the backward angular flux failed");
+                die(where);
+            }
+        }
         if (P->leakage)
             cudaMemcpyAsync(m.h->d.leakage, P->leakage, sizeof(float), cudaMemcpyHostToDevice, m.h->stream);
     }

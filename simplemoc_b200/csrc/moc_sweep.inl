@@ -120,10 +120,7 @@ static void launch_walk(const moc_handle *h, const WalkParams &w, long long n_pa
     }
 }
 
-// lane mapping of the attenuation kernel for G groups
-struct LaneMap {
-    int L, NV4, NS;
-};
+// lane mapping of the attenuation kernel for G groups (LaneMap: moc_device.cu)
 static LaneMap choose_lanes(int G, int lanes_override)
 {
     if (lanes_override == 0) {
@@ -164,6 +161,18 @@ static int launch_attenuate_mode(const moc_handle *h, const AttenuateParams &a, 
             cudaFuncSetAttribute(attenuate_kernel<L, NV4, NS, M, F, GC, C>,                                    \
                                  cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);  \
             configured = true;                                                                                 \
+        }                                                                                                      \
+        /* tables finer than the default (Input.precision below ~2.7e-5: more than 48 KB) need the opt-in   */  \
+        static size_t smem_allowed = 48 * 1024;                                                                \
+        if ((M) != 2 && smem > smem_allowed) {                                                                 \
+            if (cudaFuncSetAttribute(attenuate_kernel<L, NV4, NS, M, F, GC, C>,                                \
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { \
+                moc_set_error("exponential table of %d cells (%zu bytes) does not fit the shared memory of an SM", \
+                              a.table_n, smem);                                                                \
+                cudaGetLastError();                                                                            \
+                return MOC_EINVAL;                                                                             \
+            }                                                                                                  \
+            smem_allowed = smem;                                                                               \
         }                                                                                                      \
         attenuate_kernel<L, NV4, NS, M, F, GC, C><<<grid, 128, (M) == 2 ? 0 : smem, h->stream>>>(a);           \
     } while (0)

@@ -21,8 +21,9 @@
  *   - fine intervals are computed without the IEEE-division sequence and without conversion
  *     instructions (XU pipe): a Newton quotient on FMA units and a directed-rounding add, used
  *     only after interval_check_kernel verified it against the division for every float of the
- *     domain's height range (moc_create); the double division by cos(polar) is Markstein's
- *     correctly rounded quotient from a correctly rounded reciprocal (3 DP operations);
+ *     domain's height range (moc_create); the double division by cos(polar) is a reciprocal
+ *     product with one FMA correction (3 DP operations) that falls back to the IEEE division
+ *     whenever its result lies within 4 ulp of a float rounding boundary (div_by_cos);
  *   - s_full = length / sin(polar) (a double division, uniform over the stack) is evaluated by
  *     lane l for step 32*b + l and broadcast, instead of by every lane for every step;
  *   - records are segment-major inside a stack (slot(ray k, segment j) = base + j * Zs + k): the
@@ -122,14 +123,25 @@ __device__ __forceinline__ int interval_of(const WalkParams &w, float z)
     return FAST ? interval_by_fma<UP>(z, w.dz_interval, w.iv_rdz) : axial_interval<UP>(z, w.dz_interval);
 }
 
-// (float)(num / cos_p) for a float-valued num: Markstein's correctly rounded quotient
-// q' = q + (num - cos_p q) rcos with q = num rcos, rcos = RN(1 / cos_p)
+// (float)(num / cos_p) for a float-valued num, as solver.c:449 computes it: an IEEE double division,
+// narrowed to float.  !FAST: exactly that instruction sequence.  FAST: q' = q + (num - cos_p q) rcos with
+// q = num rcos and rcos = RN(1 / cos_p) -- three DP operations instead of the ~40 of the division.  q' is
+// within 2 ulp(double) of the true quotient (q is within 2 ulp: one rounding of rcos, one of the product; the
+// correction step with the exact FMA residual does not make it worse), and so is the IEEE quotient, hence
+// the two differ by fewer than 4 ulp and narrow to the SAME float unless q' lies within 4 ulp of a
+// float rounding boundary (the midpoint between two floats: low 29 mantissa bits = 0x10000000).  That case
+// (9 / 2^29 of all quotients) takes the IEEE division; no theorem about q' being correctly rounded is needed.
+template <bool FAST>
 __device__ __forceinline__ float div_by_cos(float num, double cos_p, double rcos)
 {
     const double a = (double)num;
+    if (!FAST) return (float)__ddiv_rn(a, cos_p);
     const double q = __dmul_rn(a, rcos);
     const double r = __fma_rn(-cos_p, q, a);
-    return (float)__fma_rn(r, rcos, q);
+    const double q2 = __fma_rn(r, rcos, q);
+    const uint32_t lo29 = (uint32_t)__double2loint(q2) & 0x1fffffffu;
+    if (lo29 - 0x0ffffffcu <= 8u) return (float)__ddiv_rn(a, cos_p);   // within 4 ulp of a tie: decide exactly
+    return (float)q2;
 }
 
 // What attenuate_fluxes derives from the height a 3D segment starts at (solver.c:38-45, 55-58,
@@ -153,8 +165,10 @@ __device__ __forceinline__ uint32_t emit_geometry(const WalkParams &w, float z_s
         iq_f = (float)iq;
     }
     float zin = __fsub_rn(z_start, __fmul_rn(w.dz_fine, __fadd_rn(iq_f, 0.5f)));
-    // iq % fai: fai_magic = floor(2^32 / fai) + 1 is exact for iq < 2^26 (fai <= 63)
-    const int fine = (unsigned)iq < (1u << 20) ? iq - (int)__umulhi((uint32_t)iq, w.fai_magic) * w.fai : iq % w.fai;
+    // iq % fai: fai_magic = floor(2^32 / fai) + 1 is exact for iq < 2^26 (2 <= fai <= 63); fai = 1 (a flat source
+    // over a single fine interval, solver.c:1040-1138) has no 32-bit reciprocal: the remainder is 0
+    const int fine = w.fai == 1 ? 0
+                   : (unsigned)iq < (1u << 20) ? iq - (int)__umulhi((uint32_t)iq, w.fai_magic) * w.fai : iq % w.fai;
     int r0 = fine, which = 0;
     if (w.axial_exp == 2) {
         if (fine == 0) { r0 = 0; zin = __fsub_rn(zin, w.dz_fine); }
@@ -310,7 +324,7 @@ __device__ __forceinline__ void walk_stack_warp(const WalkParams &w, const long 
                     } else {
                         c += UP ? 1 : -1;
                         z = (float)__dmul_rn(w.fine_dz, (double)c);   // (float)c is exact, so is (double)(float)c
-                        ds = div_by_cos(__fsub_rn(z, z_cur), cos_p, rcos);
+                        ds = div_by_cos<FAST>(__fsub_rn(z, z_cur), cos_p, rcos);
                         s = __fsub_rn(s, ds);
                         if (s <= 0.0f) finished = true;
                         if (z <= 0.0f || z >= w.node_dz_f) {
@@ -369,7 +383,7 @@ __device__ __forceinline__ void walk_stack_warp(const WalkParams &w, const long 
                     } else {
                         c += UP ? 1 : -1;
                         z = (float)__dmul_rn(w.fine_dz, (double)c);   // (float)c is exact, so is (double)(float)c
-                        ds = div_by_cos(__fsub_rn(z, z_cur), cos_p, rcos);
+                        ds = div_by_cos<FAST>(__fsub_rn(z, z_cur), cos_p, rcos);
                         s = __fsub_rn(s, ds);
                         if (s <= 0.0f) finished = true;
                         if (z <= 0.0f || z >= w.node_dz_f) {

@@ -78,8 +78,7 @@ CASES = {
     "polar2": [3, 3, 2, 3, 2, 2.0, 8.0, 8, 2, 12, 0, 1, 10, 21.42, 400.0, 0.01, 200, 0],
     "onecell": [3, 3, 1, 3, 2, 2.0, 4.0, 8, 4, 16, 0, 1, 10, 21.42, 400.0, 0.01, 200, 0],
     "zone": [3, 3, 4, 3, 2, 2.0, 400.0, 8, 4, 16, 0, 1, 10, 21.42, 400.0, 0.01, 200, 0],
-    # flat source over one and over two fine intervals per coarse one: legal in the reference, fai < 3.  CPU only so
-    # far (oracle against the reference + digests); moc_create refuses fai = 1 (DESIGN "Size limits")
+    # flat source over one and over two fine intervals per coarse one: legal in the reference, fai < 3
     "flat_f1": [3, 3, 4, 1, 0, 2.0, 4.0, 8, 4, 16, 0, 1, 10, 21.42, 400.0, 0.01, 200, 0],
     "flat_f2": [3, 3, 4, 2, 0, 2.0, 4.0, 8, 4, 16, 0, 1, 10, 21.42, 400.0, 0.01, 200, 0],
     # group counts whose pairwise_sum trees are uneven (utils.c:29-45: 33 = 16 + 17 -> 17 = 8 + 9;
@@ -212,7 +211,7 @@ class OracleCase(_Base):
                 getattr(L, "oracle_" + n).argtypes = [C.c_void_p]
             for n in ("psi", "source_data", "xs_data", "scatter_data", "polar_angles",
                       "p_weight", "z_height", "az_weight", "n_segments", "seg_lengths",
-                      "xs_index", "vol", "table_values", "leakage", "seg_count", "digest", "digest_back", "abs_flux",
+                      "xs_index", "vol", "table_values", "leakage", "seg_count", "digest", "digest_back", "abs_flux", "abs_terms",
                       "trace_track", "trace_row", "trace_ds", "trace_zstart"):
                 getattr(L, "oracle_" + n).restype = C.c_void_p
                 getattr(L, "oracle_" + n).argtypes = [C.c_void_p]
@@ -311,6 +310,13 @@ class OracleCase(_Base):
     def abs_flux(self):
         I = self.I
         return _view(self._ptr("abs_flux"), (I.n_source_regions_per_node, I.fai, I.n_egroups))
+
+    @property
+    def abs_terms(self):
+        """per element of fine_flux: sum over its tallies of the magnitudes of the terms the reference's formula
+        adds to form each tally -- the scale of the reference's own rounding error (cancellation inside a tally)"""
+        I = self.I
+        return _view(self._ptr("abs_terms"), (I.n_source_regions_per_node, I.fai, I.n_egroups))
 
     @property
     def digest(self):

@@ -196,10 +196,12 @@ def test_ray_trace_kernels_agree(built, case, walk, exact):
 
 
 @pytest.mark.parametrize("case,seed,walk", [("ragged", 2, 0), ("ragged", 4, 1), ("polar1", 2, 0), ("polar1", 2, 1),
-                                            ("polar2", 2, 0), ("onecell", 2, 0), ("zone", 2, 0), ("zone", 2, 1)])
+                                            ("polar2", 2, 0), ("onecell", 2, 0), ("zone", 2, 0), ("zone", 2, 1),
+                                            ("flat_f1", 6, 0), ("flat_f1", 6, 1), ("flat_f2", 6, 0), ("flat_f2", 6, 1)])
 def test_edge_cases(built, case, seed, walk):
     """2D tracks without segments, a single (horizontal) polar angle, one coarse axial interval,
-    one ray per z-stack: integers exact, flux within tolerance, over two sweeps and the reductions."""
+    one ray per z-stack, a flat source over one and over two fine intervals per coarse one (fai < 3,
+    solver.c:1040-1138): integers exact, flux within tolerance, over two sweeps and the reductions."""
     host, dev, oracle = make_pair(case, seed=seed, walk=walk)
     for sweep in range(2):
         assert dev.sweep() == oracle.sweep()

@@ -153,16 +153,17 @@ def test_the_model_follows_the_device_code():
 
 def test_fai_magic_remainder_is_exact():
     """emit_geometry (moc_walk_warp.cuh) takes `iq % fai` as iq - umulhi(iq, floor(2^32 / fai) + 1) * fai whenever
-    iq < 2^20, with the reciprocal held in 32 bits (moc_sweep.inl), and moc_create accepts 2 <= fai <= 63:
-    exhaustive over that whole range.  fai = 1 has no 32-bit reciprocal (2^32 + 1 wraps to 1) -- refused."""
+    iq < 2^20, with the reciprocal held in 32 bits (moc_sweep.inl), for 2 <= fai <= 63: exhaustive over that whole
+    range.  fai = 1 has no 32-bit reciprocal (2^32 + 1 wraps to 1): the kernel answers 0 without it."""
     import numpy as np
     csrc = os.path.dirname(KERNELS)
-    assert "(unsigned)iq < (1u << 20) ? iq - (int)__umulhi((uint32_t)iq, w.fai_magic) * w.fai : iq % w.fai" in \
-        open(os.path.join(csrc, "moc_walk_warp.cuh")).read()
+    walk = open(os.path.join(csrc, "moc_walk_warp.cuh")).read()
+    assert "const int fine = w.fai == 1 ? 0" in walk
+    assert ": (unsigned)iq < (1u << 20) ? iq - (int)__umulhi((uint32_t)iq, w.fai_magic) * w.fai : iq % w.fai" in walk
     assert "w.fai_magic = (unsigned int)((1ull << 32) / (unsigned long long)std::max(h->F, 1)) + 1u;" in \
         open(os.path.join(csrc, "moc_sweep.inl")).read()
     create = open(os.path.join(csrc, "moc_device.cu")).read()
-    assert "if (I->fai < 2) {" in create and "if (I->fai > 63 ||" in create
+    assert "if (I->fai < 1) {" in create and "if (I->fai > 63 ||" in create
     iq = np.arange(1 << 20, dtype=np.uint64)
 
     def remainder(fai):
@@ -171,4 +172,4 @@ def test_fai_magic_remainder_is_exact():
 
     for fai in range(2, 64):
         assert np.array_equal(remainder(fai), iq % np.uint64(fai)), fai
-    assert not np.array_equal(remainder(1), iq % np.uint64(1))      # why fai = 1 is refused
+    assert not np.array_equal(remainder(1), iq % np.uint64(1))      # why fai = 1 does not use it

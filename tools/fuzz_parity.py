@@ -31,6 +31,8 @@ while done < n_cases:
     xa, ya = int(rng.integers(2, 5)), int(rng.integers(2, 5))
     cai, fai = int(rng.integers(1, 7)), int(rng.integers(3, 7))
     axial_exp = int(rng.choice([2, 2, 2, 0]))
+    if axial_exp == 0 and rng.integers(0, 2) == 0:
+        fai = int(rng.integers(1, 3))      # the flat source also runs over one or two fine intervals (solver.c:1040-1138)
     decompose = int(rng.integers(0, 2))
     dax = int(rng.integers(1, 11)) if decompose else 1
     height = 400.0
