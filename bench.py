@@ -82,6 +82,10 @@ def parse_args():
                     help="generate the problem on the device (moc_create_synthetic); implies --no-e2e: there "
                          "are no host structures to run the drop-in call on")
     ap.add_argument("--grid", default="", help="cx,cy,cz (default: 1x1x1, 2x1x1, 2x2x1, 2x2x2)")
+    ap.add_argument("--full-size", action="store_true",
+                    help="--impl reference: sweep the WHOLE workload instead of a bounded sample (minutes per step; "
+                         "the once-per-round check of the sampled figure, profiles/)")
+    ap.add_argument("--no-full-loop", action="store_true", help="skip the e2e_full_loop leg")
     return ap.parse_args()
 
 
@@ -101,15 +105,11 @@ def workload_input(m, name, egroups=0, decomp_ax=0):
 def _workload_input(m, name):
     if name == "default":
         inp = m.default_input()
-        label = ("default strawman problem, built-in set_default_input (src/init.c:33-74): "
-                 "G=104, 120 2D segments/track")
     elif name == "default_in":
         inp = m.input_from_values(DEFAULT_IN)
-        label = "default.in as shipped (src/default.in): G=100, cai=9, 20 2D segments/track"
     else:
         inp = m.small_input()
-        label = "small problem (-s, src/init.c:77-103)"
-    return inp, label
+    return inp, WORKLOAD_LABELS[name]
 
 
 def grid_for(n, spec):
@@ -195,6 +195,30 @@ def measured_peaks():
 
 # ------------------------------------------------------------------ the reference on the host cores
 
+def reference_input_struct():
+    """ctypes image of the reference's Input (src/SimpleMOC_header.h:28-76), declared here so that the reference
+    arm does not import the product package (its process then maps oracle/_ref only)"""
+    class Input(C.Structure):
+        _fields_ = [
+            ("x_assemblies", C.c_int), ("y_assemblies", C.c_int), ("cai", C.c_int), ("fai", C.c_int),
+            ("axial_exp", C.c_int), ("radial_ray_sep", C.c_float), ("axial_z_sep", C.c_float),
+            ("n_azimuthal", C.c_int), ("n_polar_angles", C.c_int), ("n_egroups", C.c_int), ("decompose", C.c_bool),
+            ("decomp_assemblies_ax", C.c_int), ("segments_per_track", C.c_long), ("assembly_width", C.c_float),
+            ("height", C.c_float), ("domain_height", C.c_float), ("precision", C.c_float), ("mype", C.c_long),
+            ("ntracks_2D", C.c_long), ("z_stacked", C.c_int), ("ntracks", C.c_long), ("nthreads", C.c_int),
+            ("papi_event_set", C.c_int), ("n_2D_source_regions_per_assembly", C.c_long),
+            ("n_source_regions_per_node", C.c_long), ("load_tracks", C.c_bool), ("track_file", C.c_char_p),
+            ("segments_processed", C.c_long)]
+    return Input
+
+
+WORKLOAD_LABELS = {
+    "default": "default strawman problem, built-in set_default_input (src/init.c:33-74): G=104, 120 2D segments/track",
+    "default_in": "default.in as shipped (src/default.in): G=100, cai=9, 20 2D segments/track",
+    "small": "small problem (-s, src/init.c:77-103)",
+}
+
+
 class ReferenceCPU:
     """oracle/_ref/libsimplemoc_ref_omp.so: the unmodified reference, stock OpenMP flags."""
 
@@ -218,7 +242,7 @@ class ReferenceCPU:
         self.L = L
 
     def make(self, workload, nthreads, limit_tracks_2d):
-        from simplemoc_b200.api import Input
+        Input = reference_input_struct()     # the reference arm maps oracle/_ref only, never libmoc_b200.so
         path = b""
         tmp = None
         if workload == "default_in":
@@ -246,9 +270,9 @@ class ReferenceCPU:
         self.L.ref_case_destroy(h)
 
 
-def time_reference(args, steps, warmup, seconds_per_step):
+def time_reference(args, steps, warmup, seconds_per_step, full=False):
     """Times transport_sweep of the reference on a sample of `workload` sized for
-    ~seconds_per_step; returns (integrations/s, description dict)."""
+    ~seconds_per_step (full: on the whole workload); returns (integrations/s, s/step, description dict)."""
     ref = ReferenceCPU()
     cores = os.cpu_count() or 1
     # calibrate on a sliver
@@ -260,6 +284,8 @@ def time_reference(args, steps, warmup, seconds_per_step):
     rate = integ / max(t, 1e-6)
     per_2d_track = integ / probe_tracks
     want = int(max(16, seconds_per_step * rate / per_2d_track)) // 2 * 2
+    if full:
+        want = 0          # ref_case_create: 0 = every 2D track of the workload
     h, inp = ref.make(args.workload, cores, want)
     want = inp.ntracks_2D   # clipped to the full problem if the sample would exceed it
     times, integs = [], []
@@ -286,17 +312,123 @@ def run_reference(args):
         return
     # the whole run should end within a few minutes
     per_step = max(2.0, min(20.0, 150.0 / (args.steps + args.warmup)))
-    value, sec_per_step, desc = time_reference(args, args.steps, args.warmup, per_step)
-    import simplemoc_b200 as m
-    _, label = workload_input(m, args.workload)     # the reference arm runs the named workload as shipped
+    value, sec_per_step, desc = time_reference(args, args.steps, args.warmup, per_step, full=args.full_size)
+    label = WORKLOAD_LABELS[args.workload]          # the reference arm runs the named workload as shipped
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * sec_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": label, "sampled": True}, "impl": "reference",
+            "config": {"workload": label, "sampled": not args.full_size}, "impl": "reference",
             "ns_per_integration": 1e9 / value, "cpu_baseline": desc,
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     emit_line(json.dumps(finite(line), allow_nan=False))
+
+
+
+# ------------------------------------------------------------------ roofline of K1
+
+# FMA-pipe cycles one segment x one lane costs in the G = 104 instantiation of attenuate_kernel (13 groups per lane),
+# counted in the SASS of the built library (tools/sass_histogram: packed FFMA2/FMUL2/FADD2 hold the pipe for two
+# cycles per warp instruction, scalar FFMA/FMUL/FADD/IMAD for one); ncu's sm__pipe_fma_cycles_active of the same
+# launch is the cross-check (profiles/).  Keep in step with moc_attenuate.cuh.
+K1_PIPE_MIX = {"table": (210, 60), "sfu": (192, 45)}     # (packed, scalar) per segment and lane
+
+
+def k1_roofline(args, api, dev_opts, inp, state, step_ms_total, clocks, l2_probe, torch, local, world):
+    """attenuate_kernel against what bounds it.  L2-resident source slab (configs 1-4): the FP32 (FMA) pipe --
+    `frac` is the fraction of FMA-pipe cycles the launch keeps busy; HBM sits beside it (`hbm`), with the DRAM
+    traffic ncu measured against SURVEY 8(d)'s algorithmic bytes (angular flux in + out).  Source slab larger
+    than the L2 (config 5): random 128-byte DRAM gathers -- `bound` is "hbm" and `frac` the HBM fraction."""
+    G, T3 = inp.n_egroups, inp.ntracks
+    n_launch = max(args.steps, 1)
+    att_s = state["att_ms"] * 1e-3
+    att_per_launch = att_s / n_launch
+    my_integ = state["segments"] * G
+    integ_per_launch = my_integ / n_launch
+    hbm_peak, peak_src = measured_peaks()
+    # SURVEY 8(d): algorithmic HBM bytes = the angular flux of every track read and written once
+    alg_bytes = 8.0 * T3 * G
+    record_bytes = 12.0 * state["segments"] / n_launch       # K0 -> K1 segment records (this design's own stream)
+    # DRAM bytes of one launch from the committed ncu capture of this workload (profiles/), if there is one
+    traffic, traffic_src = None, None
+    if not (args.egroups or args.limit_tracks_2d) and world == 1:
+        want = "config5" if args.decomp_ax == 2 else args.workload
+        for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_K1_dram_traffic*.json")), reverse=True):
+            try:
+                with open(f) as fh:
+                    t = json.load(fh)
+                if t.get("workload") == want and t.get("exp") == args.exp:
+                    traffic, traffic_src = t["traffic"], os.path.relpath(f, ROOT)
+                    if t.get("scale_to_full"):      # captured on a slice of 2D tracks (ncu replays ~40x): per-track figure
+                        traffic *= T3 / float(t["ntracks"])
+                    break
+            except (OSError, ValueError, KeyError):
+                pass
+    Gp = (G + 31) // 32 * 32
+    gather_set = 4.0 * (2 * inp.fai + 1) * inp.n_source_regions_per_node * Gp
+    l2_size = float(torch.cuda.get_device_properties(local).L2_cache_size)
+    slab_in_dram = inp.axial_exp == 2 and dev_opts["fit_per_segment"] == 1 and gather_set > l2_size
+    hbm = {"algorithmic_bytes": alg_bytes, "segment_record_bytes": record_bytes,
+           "achieved_gbs": alg_bytes / att_per_launch / 1e9 if att_per_launch > 0 else None,
+           "peak_gbs": hbm_peak, "peak_source": peak_src}
+    hbm["frac"] = hbm["achieved_gbs"] / hbm_peak if hbm["achieved_gbs"] else None
+    if traffic:
+        hbm["traffic_over_algorithmic"] = traffic / alg_bytes
+        hbm["traffic_gbs"] = traffic / att_per_launch / 1e9 if att_per_launch > 0 else None
+        hbm["traffic_frac_of_peak"] = hbm["traffic_gbs"] / hbm_peak if hbm["traffic_gbs"] else None
+    fp32 = {"flop_per_integration": FLOP_PER_INTEGRATION,
+            "algorithmic_tflops": my_integ * FLOP_PER_INTEGRATION / att_s / 1e12 if att_s else None,
+            "peak_tflops_nominal": FP32_PEAK_TFLOPS_NOMINAL}
+    fp32["algorithmic_frac_of_nominal"] = fp32["algorithmic_tflops"] / FP32_PEAK_TFLOPS_NOMINAL if att_s else None
+    roof = {"kernel": "attenuate_kernel", "ms_per_launch": 1e3 * att_per_launch,
+            "share_of_step": state["att_ms"] / step_ms_total if step_ms_total else None,
+            "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes": alg_bytes, "hbm": hbm, "fp32": fp32,
+            "l2": {"achieved_gbs": my_integ * L2_BYTES_PER_INTEGRATION / att_s / 1e9 if att_s else None,
+                   "bytes_per_integration": L2_BYTES_PER_INTEGRATION}}
+    # the measured ceiling of the kernel's memory side: the same gathers + vector reductions on the
+    # same (L2-resident) slab without the arithmetic, timed live (moc_probe_l2_gather)
+    if isinstance(l2_probe, tuple):
+        probe_rd, probe_mix = l2_probe
+        iface = my_integ * 20.0 / att_s / 1e9 if att_s else None   # 16 B gathered + 4 B reduced per integration
+        roof["l2"].update({"sm_l2_interface_bytes_per_integration": 20, "achieved_interface_gbs": iface,
+                           "probe_gather_gbs": probe_rd / 1e9, "probe_gather_plus_red_gbs": probe_mix / 1e9,
+                           "frac_of_probe": iface / (probe_mix / 1e9) if iface else None,
+                           "probe": "moc_probe_l2_gather: K1's access pattern on the same slab, no arithmetic"})
+    elif l2_probe is not None:
+        roof["l2"]["probe_error"] = l2_probe
+    if slab_in_dram:
+        # every per-integration gather (16 B read + 8 B read-modify-write, SURVEY 8d) is a DRAM access, except for
+        # the share of the working set the L2 holds.  With a committed ncu capture `achieved` is measured DRAM
+        # traffic / launch time; without one it is the modelled figure, and says so.
+        miss = 1.0 - l2_size / gather_set
+        model = alg_bytes + record_bytes + L2_BYTES_PER_INTEGRATION * miss * integ_per_launch
+        used = traffic if traffic else model
+        roof.update({"bound": "hbm", "unit": "GB/s", "peak": hbm_peak, "peak_source": peak_src,
+                     "achieved": used / att_per_launch / 1e9 if att_per_launch > 0 else None,
+                     "achieved_from": ("ncu dram__bytes of the same launch (" + traffic_src + ")") if traffic else
+                                      f"modelled: flux + records + {L2_BYTES_PER_INTEGRATION} B/integration x L2 miss share {miss:.2f}",
+                     "modelled_bytes": model,
+                     "note": f"gather working set {gather_set / 1e6:.0f} MB > L2 {l2_size / 1e6:.0f} MB: random 128-byte DRAM gathers"})
+    else:
+        # FMA-pipe occupancy: pipe cycles the launch needs (static instruction mix x integrations) against
+        # 128 FP32 lanes per SM at the SM clock sampled during the timed region
+        n_sm = torch.cuda.get_device_properties(local).multi_processor_count
+        sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+        packed, scalar = K1_PIPE_MIX[args.exp]
+        cycles = (2 * packed + scalar) / 13.0
+        exact = G == 104 and inp.axial_exp == 2
+        peak = n_sm * 128 * sm_mhz * 1e6 * 2 / 1e12          # TFLOP/s the FMA pipes can issue at this clock
+        achieved = my_integ * cycles * 2 / att_s / 1e12 if att_s else None
+        roof.update({"bound": "fp32", "unit": "TFLOP/s", "achieved": achieved, "peak": peak,
+                     "peak_source": f"{n_sm} SMs x 128 FP32 lanes x 2 FLOP x {sm_mhz:.0f} MHz (SM clock sampled during the run)",
+                     "fma_pipe_lane_cycles_per_integration": cycles,
+                     "achieved_is": "FMA-pipe lane-cycles the kernel occupies x 2 (packed FP32x2 instructions hold the pipe two "
+                                    "cycles): frac = sm__pipe_fma_cycles_active" + ("" if exact else
+                                    " (instruction mix of the G = 104 instantiation applied to this group count: approximate)"),
+                     "note": "not HBM-bound: the gathered working set is L2-resident (hbm.frac is tiny by design); the binding "
+                             "pipe is FP32/FMA, then L1TEX/L2 gathers (l2.frac_of_probe)"})
+    roof["frac"] = roof["achieved"] / roof["peak"] if roof.get("achieved") else None
+    return roof
 
 
 # ------------------------------------------------------------------ the CUDA path
@@ -430,81 +562,25 @@ def run_moc(args):
     except Exception as e:   # diagnostics only
         l2_probe = str(e)
 
-    # ---- end to end through the reference's own entry point on host structures (rank-local)
-    e2e = None
-    if not args.no_e2e:
-        e2e = measure_e2e(args, m, api, host, dev, torch, dist, world, rank, local)
-
-    # ---- roofline of the dominant kernel (attenuate_kernel), per launch
-    att_s = state["att_ms"] * 1e-3
-    my_integ = state["segments"] * G
+    dev_opts = {"fit_per_segment": dev.get_option(api.OPT_FIT_PER_SEGMENT)}
     T3 = inp.ntracks
     n_launch = max(args.steps, 1)
-    # algorithmic HBM bytes of one launch: angular flux in and out once, segment records in,
-    # per-track offsets/counts/weights in (the gathered source rows live in L2)
-    hbm_bytes = (2 * 4 * T3 * G + 12 * (state["segments"] / n_launch) + 12 * T3)
-    # Source slabs larger than the L2 (SURVEY config 5): the per-integration gathers (16 B read + 8 B
-    # read-modify-write) are DRAM traffic too, except for the share of the working set the L2
-    # can hold; the kernel then really is HBM-bound and `frac` is its HBM fraction
-    gather_note = None
-    Gp = (G + 31) // 32 * 32
-    gather_set = 4.0 * (2 * inp.fai + 1) * inp.n_source_regions_per_node * Gp
-    l2_size = float(torch.cuda.get_device_properties(local).L2_cache_size)
-    if inp.axial_exp == 2 and dev.get_option(api.OPT_FIT_PER_SEGMENT) == 1 and gather_set > l2_size:
-        miss = 1.0 - l2_size / gather_set
-        hbm_bytes += L2_BYTES_PER_INTEGRATION * miss * (my_integ / n_launch)
-        gather_note = (f"gather working set {gather_set / 1e6:.0f} MB > L2 {l2_size / 1e6:.0f} MB: "
-                       f"{L2_BYTES_PER_INTEGRATION} B/integration x {miss:.2f} counted as HBM traffic")
-    hbm_peak, peak_src = measured_peaks()
-    att_per_launch = att_s / n_launch
-    # DRAM bytes of one launch from the committed ncu capture of this workload (profiles/), if there is one
-    traffic, traffic_src = None, None
-    if not (args.egroups or args.decomp_ax or args.limit_tracks_2d) and world == 1:
-        for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_K1_dram_traffic*.json")), reverse=True):
-            try:
-                with open(f) as fh:
-                    t = json.load(fh)
-                if t.get("workload") == args.workload and t.get("exp") == args.exp:
-                    traffic, traffic_src = t["traffic"], os.path.relpath(f, ROOT)
-                    break
-            except (OSError, ValueError, KeyError):
-                pass
-    roof = {"kernel": "attenuate_kernel", "bound": "hbm",
-            "achieved": hbm_bytes / att_per_launch / 1e9 if att_per_launch > 0 else None,
-            "peak": hbm_peak, "unit": "GB/s", "peak_source": peak_src, "traffic": traffic,
-            "traffic_source": traffic_src, "algorithmic_bytes": hbm_bytes,
-            "ms_per_launch": 1e3 * att_per_launch, "share_of_step": state["att_ms"] / ms if ms else None,
-            "fp32": {"achieved_tflops": my_integ * FLOP_PER_INTEGRATION / att_s / 1e12 if att_s else None,
-                     "peak_tflops_nominal": FP32_PEAK_TFLOPS_NOMINAL,
-                     "flop_per_integration": FLOP_PER_INTEGRATION},
-            "l2": {"achieved_gbs": my_integ * L2_BYTES_PER_INTEGRATION / att_s / 1e9 if att_s else None,
-                   "bytes_per_integration": L2_BYTES_PER_INTEGRATION},
-            "note": gather_note or "not HBM-bound: FP32 issue + L2 gather/atomic bound (DESIGN.md 'roofline')"}
-    # the measured ceiling of the kernel's memory side: the same gathers + vector reductions on the
-    # same (L2-resident) slab without the arithmetic, timed live (moc_probe_l2_gather)
-    if isinstance(l2_probe, tuple):
-        probe_rd, probe_mix = l2_probe
-        iface = my_integ * 20.0 / att_s / 1e9 if att_s else None   # 16 B gathered + 4 B reduced per integration
-        roof["l2"].update({"sm_l2_interface_bytes_per_integration": 20, "achieved_interface_gbs": iface,
-                           "probe_gather_gbs": probe_rd / 1e9, "probe_gather_plus_red_gbs": probe_mix / 1e9,
-                           "frac_of_probe": iface / (probe_mix / 1e9) if iface else None,
-                           "probe": "moc_probe_l2_gather: K1's access pattern on the same slab, no arithmetic"})
-    elif l2_probe is not None:
-        roof["l2"]["probe_error"] = l2_probe
-    roof["frac"] = roof["achieved"] / hbm_peak if roof["achieved"] else None
-    # what the kernel is actually bound by: FMA-pipe occupancy from the static instruction mix of the
-    # G = 104 instantiation (per segment and lane of 13 groups, 210 packed FP32x2
-    # instructions at 2 pipe cycles + 60 scalar FFMA/FMUL/FADD/IMAD at 1) against 128 FP32 lanes per SM at
-    # the SM clock sampled during the timed region; ncu's sm__pipe_fma_cycles_active of the same kernel is
-    # the cross-check (profiles/r01_K1_attenuate_coef_ncu_full.txt)
-    if G == 104 and inp.axial_exp == 2 and clocks and clocks.get("sm_mhz") and att_s:
-        packed, scalar = (210, 60) if args.exp == "table" else (192, 45)
-        cycles = (2 * packed + scalar) / 13.0
-        n_sm = torch.cuda.get_device_properties(local).multi_processor_count
-        lanes_per_s = n_sm * 128 * clocks["sm_mhz"] * 1e6
-        roof["fp32"].update({"fma_pipe_lane_cycles_per_integration": cycles,
-                             "frac_of_fma_pipe": my_integ * cycles / att_s / lanes_per_s,
-                             "fma_pipe_peak": f"{n_sm} SMs x 128 lanes x {clocks['sm_mhz']:.0f} MHz (sampled)"})
+
+    # ---- N > 1: is what NCCL moved what comms.c moves?  The boundary-exchange case through moc_exchange on this
+    # communicator's ranks against the all-ranks model of comms.c (pinned on the reference's own comms.c,
+    # tests/test_exchange_pin.py), before anything else is torn down
+    exchange_parity = None
+    if world > 1:
+        exchange_parity = check_exchange_parity(m, api, torch, dist, world, rank, local, (cx, cy, cz))
+
+    # ---- end to end through the reference's own entry point on host structures (rank-local)
+    e2e = None
+    full_loop = None
+    if not args.no_e2e:
+        e2e, full_loop = measure_e2e(args, m, api, host, dev, torch, dist, world, rank, local, grid)
+
+    # ---- roofline of the dominant kernel (attenuate_kernel), per launch
+    roof = k1_roofline(args, api, dev_opts, inp, state, ms, clocks, l2_probe, torch, local, world)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -533,8 +609,13 @@ def run_moc(args):
                 "phases_ms": {"count": state["count_ms"] / n_launch, "fill": state["fill_ms"] / n_launch,
                               "attenuate": state["att_ms"] / n_launch},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roof, "e2e": e2e,
-                "other_exp_mode": other,
+                "e2e_full_loop": full_loop, "other_exp_mode": other,
                 "cpu_baseline": cpu}
+        if exchange_parity is not None:
+            line["exchange_parity"] = exchange_parity
+        line["config"]["keff_feedback"] = ("k-eff of step n feeds update_sources of step n+1 (main.c:81,89); replaced by 1.0 when it "
+                                          "leaves [1e-2, 1e2] (with neighbours the reference adds un-normalised flux sums to the "
+                                          "leakage and never resets it, comms.c:120: k collapses after its single iteration)")
         if args.limit_tracks_2d:
             line["config"]["limit_tracks_2d"] = args.limit_tracks_2d
         emit_line(json.dumps(finite(line), allow_nan=False))
@@ -545,10 +626,13 @@ def run_moc(args):
         dist.destroy_process_group()
 
 
-def measure_e2e(args, m, api, host, dev, torch, dist, world, rank, local):
+def measure_e2e(args, m, api, host, dev, torch, dist, world, rank, local, grid):
     """transport_sweep(Params*, Input*) -- the reference's own prototype (src/solver.c:283) --
     on the host structures, non-resident: upload of the step's inputs from pinned host memory,
-    the sweep, download of what transport_sweep mutates; all inside the timed region."""
+    the sweep, download of what transport_sweep mutates; all inside the timed region.
+    Returns (e2e, e2e_full_loop): the second times the reference's whole iteration (main.c:57-92:
+    transport_sweep, [fast_transfer_boundary_fluxes,] renormalize_flux, update_sources, compute_keff) through
+    the five drop-in names on the same host structures, every call moving what it reads and writes."""
     L = api.lib()
     inp = host.I
     T3, G, F, N = inp.ntracks, inp.n_egroups, inp.fai, inp.n_source_regions_per_node
@@ -561,34 +645,110 @@ def measure_e2e(args, m, api, host, dev, torch, dist, world, rank, local):
     L.transport_sweep(C.byref(host.P), C.byref(I2))           # warm-up: builds the mirror
     torch.cuda.synchronize()
     mirror = L.moc_handle_of(C.byref(host.P))
+    if world > 1:
+        # the drop-in mirror is a handle of its own: it needs its own communicator for the exchange
+        buf = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            buf.copy_(torch.frombuffer(bytearray(api.nccl_unique_id()), dtype=torch.uint8))
+        dist.broadcast(buf, 0)
+        assert L.moc_comm_init(mirror, world, rank, bytes(buf.cpu().numpy().tobytes())) == 0
     stream = torch.cuda.ExternalStream(L.moc_get_stream(mirror), device=torch.device("cuda", local))
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    if dist is not None:
-        dist.barrier()
-    t0 = time.perf_counter()
-    e0.record(stream)
-    segs = 0
-    for _ in range(steps):
+
+    def timed(body):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if dist is not None:
+            dist.barrier()
+        t0 = time.perf_counter()
+        e0.record(stream)
+        segs = 0
+        for _ in range(steps):
+            segs += body()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        dt = e0.elapsed_time(e1) * 1e-3
+        if dist is not None:
+            t = torch.tensor([dt, wall], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt, wall = float(t[0].item()), float(t[1].item())
+            s = torch.tensor([segs], dtype=torch.int64, device="cuda")
+            dist.all_reduce(s, op=dist.ReduceOp.SUM)
+            segs = int(s.item())
+        return segs, dt, wall
+
+    def sweep_only():
         L.transport_sweep(C.byref(host.P), C.byref(I2))       # returns after the download completed
-        segs += I2.segments_processed
-    e1.record(stream)
-    torch.cuda.synchronize()
-    wall = time.perf_counter() - t0
-    dt = e0.elapsed_time(e1) * 1e-3
-    if dist is not None:
-        t = torch.tensor([dt, wall], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt, wall = float(t[0].item()), float(t[1].item())
-        s = torch.tensor([segs], dtype=torch.int64, device="cuda")
-        dist.all_reduce(s, op=dist.ReduceOp.SUM)
-        segs = int(s.item())
+        return I2.segments_processed
+
+    segs, dt, wall = timed(sweep_only)
     h2d = 40 * T3 + 4 * T3 * G + 4 * (2 * F + 1) * N * G     # Track image, forward flux rows, source slab
     d2h = 40 * T3 + 4 * T3 * G + 4 * F * N * G               # Track image, forward flux rows, scalar flux
+    e2e = {"value": segs * G / dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+           "steps": steps, "ms_per_step": 1e3 * dt / steps, "host_wall_ms_per_step": 1e3 * wall / steps,
+           "call": "transport_sweep(Params*, Input*) on host structures (drop-in C-ABI), CUDA events on "
+                   "the library's stream around upload + sweep + download; times the sweep only, like the "
+                   "metric (utils.c:147-155) and the reference arm -- the whole iteration is e2e_full_loop"}
+    full = None
+    if not args.no_full_loop:
+        keff = [1.0]
+
+        def iteration():
+            L.transport_sweep(C.byref(host.P), C.byref(I2))
+            if world > 1:
+                L.fast_transfer_boundary_fluxes(host.P, I2, grid)
+            L.renormalize_flux(host.P, I2, grid)
+            k = keff[0]
+            L.update_sources(host.P, I2, k if (k == k and 1e-2 < abs(k) < 1e2) else 1.0)
+            keff[0] = L.compute_keff(host.P, I2, grid)
+            return I2.segments_processed
+
+        iteration()                                            # warm-up of the four other entry points
+        segs, dt, wall = timed(iteration)
+        full = {"value": segs * G / dt, "unit": UNIT, "steps": steps, "ms_per_step": 1e3 * dt / steps,
+                "host_wall_ms_per_step": 1e3 * wall / steps,
+                "call": "the reference's iteration (main.c:57-92) through the five drop-in names on host structures, "
+                        "host authoritative between the calls (moc_set_resident(0), the default)"}
     L.moc_release(C.byref(host.P))
-    return {"value": segs * G / dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-            "steps": steps, "ms_per_step": 1e3 * dt / steps, "host_wall_ms_per_step": 1e3 * wall / steps,
-            "call": "transport_sweep(Params*, Input*) on host structures (drop-in C-ABI), CUDA events on "
-                    "the library's stream around upload + sweep + download"}
+    return e2e, full
+
+
+def check_exchange_parity(m, api, torch, dist, world, rank, local, dims):
+    """The boundary exchange of this run's ranks against the CPU model of comms.c (oracle_exchange, pinned bit for
+    bit on the reference's own comms.c by tests/test_exchange_pin.py): a small problem with one 10 000-track
+    message per face, every rank's own domain swept on its GPU, moc_exchange over NCCL, slab and leakage compared
+    on every rank.  The oracle is the checker here, outside every timed region."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import numpy as np
+    from oracle_lib import CASES, CommGrid, OracleCase, make_grid as oracle_grid
+    vals = CASES["exch"]
+    host = m.HostProblem(m.derive(m.input_from_values(vals)), seed=21 + rank)
+    dev = m.DeviceProblem(host, device=local)
+    buf = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        buf.copy_(torch.frombuffer(bytearray(api.nccl_unique_id()), dtype=torch.uint8))
+    dist.broadcast(buf, 0)
+    dev.comm_init(world, rank, bytes(buf.cpu().numpy().tobytes()))
+    cases = [OracleCase(vals, seed=21 + r) for r in range(world)]
+    for c in cases:
+        c.sweep()
+    ok = dev.sweep() == cases[rank].I.segments_processed
+    dev.set(api.ARR_PSI, cases[rank].psi)               # identical slabs in, so the comparison is bit for bit
+    grids = (CommGrid * world)(*[oracle_grid(*dims, r) for r in range(world)])
+    hs = (C.c_void_p * world)(*[c.h for c in cases])
+    ok = ok and OracleCase.lib().oracle_exchange(hs, grids, world) == 0
+    dev.exchange(m.make_grid(*dims, rank))
+    ok = ok and bool(np.array_equal(dev.get(api.ARR_PSI), cases[rank].psi))
+    ok = ok and dev.leakage == float(cases[rank].leakage[0])
+    moved = int((cases[rank].psi != 0).sum())
+    flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    dev.close(); host.close()
+    for c in cases:
+        c.close()
+    verdict = "bit-exact" if int(flag.item()) == 1 else "MISMATCH"
+    return {"result": verdict, "ranks": world, "grid": "x".join(str(d) for d in dims),
+            "checked": "flux slab after moc_exchange and leakage on every rank == oracle_exchange (comms.c:5-196 model, "
+                       "pinned on the reference's own comms.c under an in-process MPI)", "case": "exch (96 000 tracks, G = 8)"}
 
 
 _RESULT_FD = None

@@ -82,10 +82,79 @@ static void pin_host_slabs(Mirror &m, const HostLayout &L)
     exit(1);
 }
 
-// Find (or build) the device mirror of a host Params.  Non-resident mode re-uploads the
-// mutable state on every call (host is authoritative); resident mode uploads once.
-static Mirror &mirror_for(const Params *P, const Input *I, HostLayout &L, bool need_backward_psi,
-                          const char *where, bool caller_streams = false)
+// What a drop-in call reads from (uploads) or writes to (downloads) the host structures.  The host is
+// authoritative between calls (moc_set_resident(0), the default): every call moves exactly the mutable state the
+// reference function of the same name reads and writes -- not the whole problem.  Static data (2D tracks, polar
+// angles, weights, materials, volumes, the table) travels once, when the mirror is built.
+enum {
+    PART_TRACKS = 1,    // ray heights (inside the 40-byte Track image)
+    PART_PSI_F = 2,     // forward angular flux rows
+    PART_PSI_B = 4,     // backward angular flux rows
+    PART_SOURCE = 8,    // fine_source
+    PART_FLUX = 16,     // fine_flux
+    PART_SIGT = 32,     // sigT
+    PART_LEAKAGE = 64,
+    PART_PSI_HEAD = 128 // the leading floats of the flux slab the boundary exchange moves (comms.c:100-183)
+};
+
+static long long exchange_head_floats(const moc_handle *h, const CommGrid *grid)
+{
+    const long n_ops = moc_exchange_plan(&h->I, grid, nullptr, 0);
+    if (n_ops <= 0) return 0;
+    return std::min<long long>((long long)n_ops * 10000ll * h->G, 2ll * h->T3 * h->G);
+}
+
+static int move_parts(moc_handle *h, const HostLayout &L, const Params *P, int parts, bool up, long long head_floats = 0)
+{
+    const size_t T3 = (size_t)h->T3, G = (size_t)h->G, N = (size_t)h->N, F = (size_t)h->F;
+    const cudaMemcpyKind kind = up ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
+    const int threads = 256;
+    if (parts & PART_TRACKS) {
+        int rc = need_track_image(h);
+        if (rc) return rc;
+        if (up) {
+            CUDA_TRY(cudaMemcpyAsync(h->d.track_image, L.tracks, sizeof(TrackImage) * T3, kind, h->stream));
+            unpack_tracks_kernel<<<(unsigned)((T3 + threads - 1) / threads), threads, 0, h->stream>>>(
+                h->d.track_image, (long long)T3, h->d.p_weight, h->d.z_height);
+        } else {
+            patch_tracks_kernel<<<(unsigned)((T3 + threads - 1) / threads), threads, 0, h->stream>>>(
+                h->d.track_image, (long long)T3, h->d.z_height);
+            CUDA_TRY(cudaMemcpyAsync((void *)L.tracks, h->d.track_image, sizeof(TrackImage) * T3, kind, h->stream));
+        }
+        h->launch_count++;
+    }
+    if ((parts & PART_PSI_F) && (parts & PART_PSI_B)) {
+        if (up) CUDA_TRY(cudaMemcpyAsync(h->d.psi, L.psi, sizeof(float) * 2 * T3 * G, kind, h->stream));
+        else CUDA_TRY(cudaMemcpyAsync(L.psi, h->d.psi, sizeof(float) * 2 * T3 * G, kind, h->stream));
+    } else if (parts & (PART_PSI_F | PART_PSI_B)) {
+        const size_t off = (parts & PART_PSI_B) ? G : 0;   // one row of every [t][2][G] pair: pitch 2 G floats
+        if (up) CUDA_TRY(cudaMemcpy2DAsync(h->d.psi + off, sizeof(float) * 2 * G, L.psi + off, sizeof(float) * 2 * G,
+                                           sizeof(float) * G, T3, kind, h->stream));
+        else CUDA_TRY(cudaMemcpy2DAsync(L.psi + off, sizeof(float) * 2 * G, h->d.psi + off, sizeof(float) * 2 * G,
+                                        sizeof(float) * G, T3, kind, h->stream));
+    } else if ((parts & PART_PSI_HEAD) && head_floats > 0) {
+        if (up) CUDA_TRY(cudaMemcpyAsync(h->d.psi, L.psi, sizeof(float) * (size_t)head_floats, kind, h->stream));
+        else CUDA_TRY(cudaMemcpyAsync(L.psi, h->d.psi, sizeof(float) * (size_t)head_floats, kind, h->stream));
+    }
+    // the source slab: fine_source rows [0, NF), fine_flux rows [NF, 2NF), sigT rows [2NF, 2NF + N)
+    struct { int part; size_t row0, rows; } slab[3] = {{PART_SOURCE, 0, N * F}, {PART_FLUX, N * F, N * F}, {PART_SIGT, 2 * N * F, N}};
+    for (const auto &q : slab)
+        if (parts & q.part) {
+            if (up) CUDA_TRY(slab_to_device(h, q.row0, q.rows, L.src + q.row0 * G));
+            else CUDA_TRY(slab_to_host(h, q.row0, q.rows, L.src + q.row0 * G));
+        }
+    if ((parts & PART_LEAKAGE) && P->leakage) {
+        if (up) CUDA_TRY(cudaMemcpyAsync(h->d.leakage, P->leakage, sizeof(float), kind, h->stream));
+        else CUDA_TRY(cudaMemcpyAsync(P->leakage, h->d.leakage, sizeof(float), kind, h->stream));
+    }
+    CUDA_TRY(cudaGetLastError());
+    return MOC_OK;
+}
+
+// Find (or build) the device mirror of a host Params.  Non-resident mode uploads `reads` (PART_* mask) on every
+// call (host is authoritative); resident mode uploads everything once, when the mirror is built.
+static Mirror &mirror_for(const Params *P, const Input *I, HostLayout &L, int reads, const char *where,
+                          const CommGrid *grid = nullptr)
 {
     std::lock_guard<std::mutex> lock(g_mirror_mutex);
     Mirror &m = g_mirrors[(const void *)P->tracks];
@@ -130,34 +199,70 @@ static Mirror &mirror_for(const Params *P, const Input *I, HostLayout &L, bool n
         m.host_src = L.src;
     }
     if (created) pin_host_slabs(m, L);
-    if (created || !g_resident) {
-        // caller_streams: the non-resident transport_sweep moves the mutable state itself, chunk by
-        // chunk, overlapped with the kernels (sweep_core); nothing to upload here
-        if (!(caller_streams && !g_resident)) {
-            if (upload_mutable(m.h, L, created || need_backward_psi)) die(where);
-        } else if (created) {
-            // the streamed sweep moves forward rows only: a new mirror still needs the backward rows once (they are
-            // scaled by renormalize_flux and moved by the exchange if the caller later switches to resident mode)
-            const size_t T3 = (size_t)m.h->T3, G = (size_t)m.h->G;
-            if (cudaMemcpy2DAsync(m.h->d.psi + G, sizeof(float) * 2 * G, L.psi + G, sizeof(float) * 2 * G, sizeof(float) * G,
-                                  T3, cudaMemcpyHostToDevice, m.h->stream) != cudaSuccess) {
-                moc_set_error("upload of the backward angular flux failed");
-                die(where);
-            }
-        }
-        if (P->leakage)
-            cudaMemcpyAsync(m.h->d.leakage, P->leakage, sizeof(float), cudaMemcpyHostToDevice, m.h->stream);
-    }
+    // a new mirror takes the whole mutable state once (whatever this call reads): later calls, and a later switch to
+    // resident mode, find every array defined
+    int parts = reads;
+    if (created) parts = PART_TRACKS | PART_PSI_F | PART_PSI_B | PART_SOURCE | PART_FLUX | PART_SIGT | PART_LEAKAGE;
+    else if (g_resident) parts = 0;
+    if (parts && move_parts(m.h, L, P, parts, true, (parts & PART_PSI_HEAD) && grid ? exchange_head_floats(m.h, grid) : 0))
+        die(where);
     return m;
+}
+
+// Wait for the stream (downloads included); the reference's functions return when their results are in place.
+static void finish(moc_handle *h, const char *where)
+{
+    if (cudaStreamSynchronize(h->stream) != cudaSuccess) {
+        moc_set_error("%s: %s", where, cudaGetErrorString(cudaGetLastError()));
+        die(where);
+    }
+}
+
+// renormalize_flux on host structures (solver.c:1143-1230), host authoritative: the scalar flux (14 MB on the default
+// problem) goes up, is reduced and scaled and comes back; the angular flux -- every forward and backward row, 12.9 GB
+// -- travels in chunks: upload of chunk c+1, scaling of chunk c and download of chunk c-1 overlap on three streams.
+static int renormalize_streamed(Mirror &m, const HostLayout &L, const Params *P)
+{
+    moc_handle *h = m.h;
+    int rc;
+    if ((rc = renormalize_scalar_flux(h))) return rc;                 // the scalar flux was uploaded by mirror_for
+    if ((rc = move_parts(h, L, P, PART_FLUX, false))) return rc;
+    if (!h->up_stream) CUDA_TRY(cudaStreamCreateWithFlags(&h->up_stream, cudaStreamNonBlocking));
+    if (!h->down_stream) CUDA_TRY(cudaStreamCreateWithFlags(&h->down_stream, cudaStreamNonBlocking));
+    const long long n = 2 * h->T3 * h->G;
+    const long long chunks = std::max<long long>(1, std::min<long long>(h->stream_chunks, n / 4096 + 1));
+    const long long per = ((n + chunks - 1) / chunks + 3) / 4 * 4;
+    size_t ev_next = 0;
+    cudaEvent_t e_begin, e_home;
+    if ((rc = event_at(h, ev_next++, &e_begin))) return rc;
+    CUDA_TRY(cudaEventRecord(e_begin, h->stream));
+    CUDA_TRY(cudaStreamWaitEvent(h->up_stream, e_begin, 0));
+    for (long long first = 0; first < n; first += per) {
+        const long long count = std::min(per, n - first);
+        cudaEvent_t e_up, e_done;
+        if ((rc = event_at(h, ev_next++, &e_up))) return rc;
+        if ((rc = event_at(h, ev_next++, &e_done))) return rc;
+        CUDA_TRY(cudaMemcpyAsync(h->d.psi + first, L.psi + first, sizeof(float) * (size_t)count, cudaMemcpyHostToDevice, h->up_stream));
+        CUDA_TRY(cudaEventRecord(e_up, h->up_stream));
+        CUDA_TRY(cudaStreamWaitEvent(h->stream, e_up, 0));
+        scale_psi_range(h, first, count, h->stream);
+        CUDA_TRY(cudaEventRecord(e_done, h->stream));
+        CUDA_TRY(cudaStreamWaitEvent(h->down_stream, e_done, 0));
+        CUDA_TRY(cudaMemcpyAsync(L.psi + first, h->d.psi + first, sizeof(float) * (size_t)count, cudaMemcpyDeviceToHost, h->down_stream));
+    }
+    if ((rc = event_at(h, ev_next++, &e_home))) return rc;
+    CUDA_TRY(cudaEventRecord(e_home, h->down_stream));
+    CUDA_TRY(cudaStreamWaitEvent(h->stream, e_home, 0));
+    CUDA_TRY(cudaGetLastError());
+    return MOC_OK;
 }
 
 extern "C" void transport_sweep(Params *params, Input *I)
 {
     HostLayout L;
-    Mirror &m = mirror_for(params, I, L, false, "transport_sweep", true);
+    // non-resident: the sweep moves its own inputs and outputs, chunk by chunk, overlapped with the kernels (sweep_core)
+    Mirror &m = mirror_for(params, I, L, 0, "transport_sweep");
     long segs = 0;
-    // non-resident: uploads, kernels and downloads are pipelined inside the sweep; the call
-    // returns after the last byte is back in the host structures
     const CommGrid *ahead = nullptr;
     if (g_resident && g_dropin_grid_set) {
         const int *nb = &g_dropin_grid.x_pos_src;
@@ -175,26 +280,28 @@ extern "C" void renormalize_flux(Params params, Input I, CommGrid grid)
 {
     (void)grid;
     HostLayout L;
-    Mirror &m = mirror_for(&params, &I, L, true, "renormalize_flux");
-    if (moc_renormalize(m.h)) die("renormalize_flux");
-    if (g_resident) m.dirty_all = true;
-    else if (download_into(m.h, L, &params, 2)) die("renormalize_flux");
+    // reads the scalar flux (here) and every angular flux (streamed below)
+    Mirror &m = mirror_for(&params, &I, L, PART_FLUX, "renormalize_flux");
+    if (g_resident) {
+        if (moc_renormalize(m.h)) die("renormalize_flux");
+        m.dirty_all = true;
+        return;
+    }
+    if (renormalize_streamed(m, L, &params)) die("renormalize_flux");
+    finish(m.h, "renormalize_flux");
 }
 
 extern "C" float update_sources(Params params, Input I, float keff)
 {
     HostLayout L;
-    Mirror &m = mirror_for(&params, &I, L, false, "update_sources");
+    // reads the scalar flux and the old sources (residual, solver.c:1290-1297), writes the sources
+    Mirror &m = mirror_for(&params, &I, L, PART_FLUX | PART_SOURCE, "update_sources");
     float res = 0.f;
     if (moc_update_sources(m.h, keff, &res)) die("update_sources");
     if (g_resident) m.dirty_all = true;
     else {
-        // only fine_source changes
-        if (slab_to_host(m.h, 0, (size_t)m.h->N * m.h->F, L.src) != cudaSuccess ||
-            cudaStreamSynchronize(m.h->stream) != cudaSuccess) {
-            moc_set_error("download of fine_source failed");
-            die("update_sources");
-        }
+        if (move_parts(m.h, L, &params, PART_SOURCE, false)) die("update_sources");
+        finish(m.h, "update_sources");
     }
     return res;
 }
@@ -203,7 +310,7 @@ extern "C" float compute_keff(Params params, Input I, CommGrid grid)
 {
     (void)grid;
     HostLayout L;
-    Mirror &m = mirror_for(&params, &I, L, false, "compute_keff");
+    Mirror &m = mirror_for(&params, &I, L, PART_FLUX | PART_LEAKAGE, "compute_keff");
     float k = 0.f;
     if (moc_compute_keff(m.h, &k)) die("compute_keff");
     return k;
@@ -212,7 +319,8 @@ extern "C" float compute_keff(Params params, Input I, CommGrid grid)
 extern "C" void fast_transfer_boundary_fluxes(Params params, Input I, CommGrid grid)
 {
     HostLayout L;
-    Mirror &m = mirror_for(&params, &I, L, true, "fast_transfer_boundary_fluxes");
+    // reads and writes the leading chunks of the flux slab (comms.c:100-183) and the leakage
+    Mirror &m = mirror_for(&params, &I, L, PART_PSI_HEAD | PART_LEAKAGE, "fast_transfer_boundary_fluxes", &grid);
     if (g_resident && m.exchanged && g_dropin_grid_set && memcmp(&grid, &g_dropin_grid, sizeof(CommGrid)) == 0) {
         m.exchanged = false;   // done under the sweep (moc_dropin_set_grid)
         m.dirty_all = true;
@@ -220,7 +328,11 @@ extern "C" void fast_transfer_boundary_fluxes(Params params, Input I, CommGrid g
     }
     if (moc_exchange(m.h, &grid)) die("fast_transfer_boundary_fluxes");
     if (g_resident) m.dirty_all = true;
-    else if (download_into(m.h, L, &params, 2)) die("fast_transfer_boundary_fluxes");
+    else {
+        if (move_parts(m.h, L, &params, PART_PSI_HEAD | PART_LEAKAGE, false, exchange_head_floats(m.h, &grid)))
+            die("fast_transfer_boundary_fluxes");
+        finish(m.h, "fast_transfer_boundary_fluxes");
+    }
 }
 
 extern "C" int moc_sync_to_host(Params *params)

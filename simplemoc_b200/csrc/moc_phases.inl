@@ -20,10 +20,9 @@ static SourceParams source_params(const moc_handle *h)
 
 static int allreduce_scalars(moc_handle *h, float *dev, int count);   // comms section
 
-extern "C" int moc_renormalize(moc_handle *h)
+// renormalize_flux, first half (solver.c:1143-1214): total fission rate (all ranks), scalar flux scaled
+static int renormalize_scalar_flux(moc_handle *h)
 {
-    if (!h) return MOC_EINVAL;
-    CUDA_TRY(cudaSetDevice(h->device));
     const SourceParams p = source_params(h);
     const unsigned rb = (unsigned)((h->N + 127) / 128);
     region_fission_rate_kernel<<<rb, 128, 0, h->stream>>>(p, h->d.per_region_a);
@@ -34,11 +33,30 @@ extern "C" int moc_renormalize(moc_handle *h)
     }
     const long long cells = h->N * h->F * h->Gp;
     scale_flux_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, h->stream>>>(p, h->d.scalars);
-    const long long n = 2 * h->T3 * h->G;
-    const long long n4 = n / 4;
-    scale_psi_kernel<<<148 * 8, 256, 0, h->stream>>>(reinterpret_cast<float4 *>(h->d.psi), n4, h->d.psi + 4 * n4,
-                                                    (int)(n - 4 * n4), h->d.scalars);
-    h->launch_count += 4;
+    h->launch_count += 3;
+    CUDA_TRY(cudaGetLastError());
+    return MOC_OK;
+}
+
+// renormalize_flux, second half (solver.c:1219-1226): floats [first, first + count) of the angular-flux slab
+// *= 1 / (total fission rate); first must be a multiple of 4
+static void scale_psi_range(moc_handle *h, long long first, long long count, cudaStream_t st)
+{
+    if (count <= 0) return;
+    const long long n4 = count / 4;
+    const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(148 * 8, (n4 + 255) / 256));
+    scale_psi_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<float4 *>(h->d.psi + first), n4, h->d.psi + first + 4 * n4,
+                                           (int)(count - 4 * n4), h->d.scalars);
+    h->launch_count++;
+}
+
+extern "C" int moc_renormalize(moc_handle *h)
+{
+    if (!h) return MOC_EINVAL;
+    CUDA_TRY(cudaSetDevice(h->device));
+    int rc = renormalize_scalar_flux(h);
+    if (rc) return rc;
+    scale_psi_range(h, 0, 2 * h->T3 * h->G, h->stream);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     return MOC_OK;

@@ -121,7 +121,7 @@ def _view(ptr, shape, dtype=np.float32):
     if n == 0:
         return np.zeros(shape, dtype=dtype)
     ctype = {np.float32: C.c_float, np.int32: C.c_int, np.int64: C.c_long,
-             np.uint32: C.c_uint32, np.uint64: C.c_uint64}[dtype]
+             np.uint32: C.c_uint32, np.uint64: C.c_uint64, np.float64: C.c_double}[dtype]
     arr = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ctype)), shape=(n,))
     return arr.reshape(shape)
 
@@ -189,6 +189,13 @@ class OracleCase(_Base):
             L = C.CDLL(ensure_oracle_built(), mode=C.RTLD_LOCAL)
             L.oracle_create.restype = C.c_void_p
             L.oracle_create.argtypes = [C.POINTER(Input), C.c_uint64]
+            L.oracle_create_geometry.restype = C.c_void_p
+            L.oracle_create_geometry.argtypes = [C.POINTER(Input), C.c_uint64]
+            L.oracle_sweep_reversed.restype = C.c_long
+            L.oracle_sweep_reversed.argtypes = [C.c_void_p]
+            for n in ("psi64", "flux64"):
+                getattr(L, "oracle_" + n).restype = C.c_void_p
+                getattr(L, "oracle_" + n).argtypes = [C.c_void_p]
             L.oracle_destroy.argtypes = [C.c_void_p]
             L.oracle_derive.argtypes = [C.POINTER(Input)]
             L.oracle_sweep.restype = C.c_long
@@ -211,7 +218,7 @@ class OracleCase(_Base):
                 getattr(L, "oracle_" + n).argtypes = [C.c_void_p]
             for n in ("psi", "source_data", "xs_data", "scatter_data", "polar_angles",
                       "p_weight", "z_height", "az_weight", "n_segments", "seg_lengths",
-                      "xs_index", "vol", "table_values", "leakage", "seg_count", "digest", "digest_back", "abs_flux", "abs_terms",
+                      "xs_index", "vol", "table_values", "leakage", "seg_count", "digest", "digest_back", "abs_flux", "abs_terms", "abs_psi",
                       "trace_track", "trace_row", "trace_ds", "trace_zstart"):
                 getattr(L, "oracle_" + n).restype = C.c_void_p
                 getattr(L, "oracle_" + n).argtypes = [C.c_void_p]
@@ -224,14 +231,16 @@ class OracleCase(_Base):
             cls._lib = L
         return cls._lib
 
-    def __init__(self, values, seed=1, exp_mode=0, limit_tracks_2D=0, track_file=None):
+    def __init__(self, values, seed=1, exp_mode=0, limit_tracks_2D=0, track_file=None, geometry_only=False):
+        """exp_mode 0: the reference's table, 1: 1 - expf(-x), 2: the attenuation in double with exp() (psi64 / flux64).
+        geometry_only: ray trace, source-region draws and digest only -- no flux or material arrays (full-size pins)"""
         L = self.lib()
         inp = input_from_values(values, track_file)
         L.oracle_derive(C.byref(inp))
         if limit_tracks_2D and limit_tracks_2D < inp.ntracks_2D:
             inp.ntracks_2D = 2 * (limit_tracks_2D // 2)
             inp.ntracks = inp.ntracks_2D * inp.n_polar_angles * inp.z_stacked
-        self.h = L.oracle_create(C.byref(inp), seed)
+        self.h = (L.oracle_create_geometry if geometry_only else L.oracle_create)(C.byref(inp), seed)
         if not self.h:
             raise RuntimeError(f"oracle_create failed (track file {track_file!r})")
         L.oracle_set_exp_mode(self.h, exp_mode)
@@ -319,11 +328,31 @@ class OracleCase(_Base):
         return _view(self._ptr("abs_terms"), (I.n_source_regions_per_node, I.fai, I.n_egroups))
 
     @property
+    def abs_psi(self):
+        """the same scale for the angular flux, carried along every track (a running error bound)"""
+        I = self.I
+        return _view(self._ptr("abs_psi"), (I.ntracks, 2, I.n_egroups))
+
+    @property
     def digest(self):
         return _view(self._ptr("digest"), (4,), np.uint64)
 
     def sweep(self):
         return self.lib().oracle_sweep(self.h)
+
+    def sweep_reversed(self):
+        """the same sweep, 2D tracks in reverse order: same draws and ray states, tallies added in another order"""
+        return self.lib().oracle_sweep_reversed(self.h)
+
+    @property
+    def psi64(self):
+        T2, P, Z, T3, G, F, N = self._sizes()
+        return _view(self._ptr("psi64"), (T3, 2, G), np.float64)
+
+    @property
+    def flux64(self):
+        T2, P, Z, T3, G, F, N = self._sizes()
+        return _view(self._ptr("flux64"), (N, F, G), np.float64)
 
     def two_way_sweep(self):
         """solver.c:556-891 (the v1 sweep, forward + backward flux)"""

@@ -18,7 +18,7 @@ import pytest
 import simplemoc_b200 as m
 from simplemoc_b200 import api
 from oracle_lib import INPUT_FILE_FIELDS, OracleCase
-from test_gpu_parity import TOL, check_state
+from test_gpu_parity import NOISE_CAP, TOL, check_state
 
 pytestmark = pytest.mark.gpu
 
@@ -78,7 +78,7 @@ def test_baseline_shape_slice(built, name):
     assert np.array_equal(dev.get(api.ARR_SEG_COUNT), oracle.seg_count)
     assert np.array_equal(dev.get(api.ARR_QSR_DIGEST), oracle.digest)
     assert np.array_equal(dev.get(api.ARR_Z_HEIGHT), oracle.z_height)
-    check_state(dev, oracle, f"{name} sweep", noise_cap=256)
+    check_state(dev, oracle, f"{name} sweep", noise_cap=NOISE_CAP)
     dev.renormalize(); oracle.renormalize()
     check_state(dev, oracle, f"{name} renormalize")
     r_gpu, r_cpu = dev.update_sources(1.0), oracle.update_sources(1.0)

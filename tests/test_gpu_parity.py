@@ -12,8 +12,23 @@ from oracle_lib import CASES, OracleCase, frac_within, noise_units, rel_l2
 pytestmark = pytest.mark.gpu
 
 TOL = 1e-4          # north_star: scalar flux and k-eff within 1e-4 relative (FP32)
+# Element-wise floors.  Every one of them is anchored in profiles/r02_tolerance_anchor.md (tools/tolerance_anchor.py):
+# the same statistics for reference-vs-reference -- the unmodified reference compiled -O2 against -Ofast -mfma, and
+# the oracle against itself with the tallies added in reverse order -- on the same 11 cases and the same three sweeps.
+#                                     reference vs reference (worst case)      GPU vs oracle     floor asserted here
+#   first sweep, bare 1e-4            0.99789 (-Ofast)  0.99898 (reversed)     0.99891           FRAC - 0.001 = 0.998
+#   first sweep, 1e-4 or 16 eps       0.99945           1.00000                0.99989           FRAC = 0.999
+#   sources after update_sources      0.99508           0.99661                0.99828           0.995
+#   second sweep, free-running        0.99482           0.99483                0.99630           SECOND = 0.985 (*)
+#   sweep from identical state        0.99319           0.99974                0.99946           0.998
+#   worst element / running scale     3.4e6 eps         0.7 eps                3.5 eps           NOISE_CAP = 64 eps
+# i.e. each floor is at least as strict as what the reference's own optimised build achieves against its -O2 build.
+# (*) free-running sweeps amplify history: over 12 runs of unchanged GPU code the fraction spread 0.989 .. 0.997 on
+# "tiny" (profiles/r01_parity_spread.log), and reference-vs-reference k-eff differs by 1.3e-2 at that point.
 FRAC = 0.999
+SECOND = 0.985
 NOISE_UNITS = 16    # roundings of an element's own accumulation that count as agreement (check_state)
+NOISE_CAP = 64      # no element further than this many roundings of its running error scale (oracle abs_terms)
 
 
 def make_pair(case, seed, exp_mode=0, batch=0, lanes=0, walk=0, exact=False, track_file=None):
@@ -57,12 +72,15 @@ def check_state(dev, oracle, what, frac_floor=FRAC, noise_cap=None):
         else:
             assert frac >= frac_floor, f"{what}: {name} only {frac:.5f} of elements within {TOL}"
     if noise_cap is not None:
-        # every scalar-flux element is within 1e-4 relative OR within rounding noise of its own
-        # accumulation (|diff| <= noise_cap * eps * sum|tally|): no element is simply wrong
+        # No element is simply wrong: each is within 1e-4 relative OR within noise_cap roundings of the scale its
+        # value is computed at -- the oracle's running error scale (abs_terms: the magnitudes of every term the
+        # reference's formula adds, carried along the track; oracle/moc_oracle.c).  The sum of |tally| alone is not
+        # that scale: the terms INSIDE one tally cancel too (a slice of config 5 has scalar-flux elements with a
+        # single tally of 9e-9 formed from terms of 0.16, profiles/r02_diag_worst_elements.log).
         rel_ok = np.abs(flux.astype(np.float64) - oracle.fine_flux) <= TOL * np.abs(oracle.fine_flux)
-        units = noise_units(flux, oracle.fine_flux, oracle.abs_flux).reshape(flux.shape)
+        units = noise_units(flux, oracle.fine_flux, oracle.abs_terms).reshape(flux.shape)
         worst = units[~rel_ok].max() if (~rel_ok).any() else 0.0
-        assert worst <= noise_cap, f"{what}: an element is off by {worst:.0f} eps*accumulation"
+        assert worst <= noise_cap, f"{what}: an element is off by {worst:.0f} eps x its running error scale"
 
 
 @pytest.mark.parametrize("case", ["tiny", "mini104", "tiny_flat", "odd", "mini_default_in"])
@@ -73,7 +91,7 @@ def test_sweep_table_mode(built, case):
     assert np.array_equal(dev.get(api.ARR_SEG_COUNT), oracle.seg_count)   # per 3D track
     assert np.array_equal(dev.get(api.ARR_QSR_DIGEST), oracle.digest)     # (serial idx, FSR row) pairs
     assert np.array_equal(dev.get(api.ARR_Z_HEIGHT), oracle.z_height)     # ray state after the sweep
-    check_state(dev, oracle, f"{case} sweep", noise_cap=256)
+    check_state(dev, oracle, f"{case} sweep", noise_cap=NOISE_CAP)
     # the rest of the iteration (main.c:73-91)
     dev.renormalize(); oracle.renormalize()
     check_state(dev, oracle, f"{case} renormalize")
@@ -94,7 +112,7 @@ def test_sweep_table_mode(built, case):
     assert np.array_equal(dev.get(api.ARR_SEG_COUNT), oracle.seg_count)
     assert np.array_equal(dev.get(api.ARR_QSR_DIGEST), oracle.digest)
     assert np.array_equal(dev.get(api.ARR_Z_HEIGHT), oracle.z_height)
-    check_state(dev, oracle, f"{case} second sweep, free-running", frac_floor=0.97)
+    check_state(dev, oracle, f"{case} second sweep, free-running", frac_floor=SECOND)
     # ... and the element-wise criterion is asked of a third sweep that starts from the oracle's own
     # state (the reductions are bit-exact on identical input, test_reductions_bit_exact_...): what is
     # compared is then one sweep's arithmetic on iterated (heavy-tailed) sources, not amplified history
@@ -151,7 +169,7 @@ def test_fit_per_segment_path(built, case):
     assert dev.get_option(api.OPT_FIT_PER_SEGMENT) == 1
     assert dev.sweep() == oracle.sweep()
     assert np.array_equal(dev.get(api.ARR_QSR_DIGEST), oracle.digest)
-    check_state(dev, oracle, f"{case} fit per segment", noise_cap=256)
+    check_state(dev, oracle, f"{case} fit per segment", noise_cap=NOISE_CAP)
     dev.close(); host.close(); oracle.close()
 
 
@@ -169,7 +187,7 @@ def test_emitting_pass_under_the_attenuation_is_invisible(built, case, ctas, bat
         assert np.array_equal(dev.get(api.ARR_QSR_DIGEST), oracle.digest)
         assert np.array_equal(dev.get(api.ARR_Z_HEIGHT), oracle.z_height)
         if sweep == 0:
-            check_state(dev, oracle, f"{case} overlapped emit", noise_cap=256)
+            check_state(dev, oracle, f"{case} overlapped emit", noise_cap=NOISE_CAP)
     dev.close(); host.close(); oracle.close()
 
 
@@ -225,18 +243,38 @@ def test_lane_mappings_agree(built, lanes):
     dev.close(); host.close(); oracle.close()
 
 
-def test_sfu_mode_against_exact_exp_oracle(built):
-    """SFU exponential (__expf) against the oracle's libm expf variant.  With exact
-    exponentials the reference's FP32 formula is dominated by cancellation noise
-    ('exponential modes'), so this comparison is informational: it must
-    agree on every integer and stay within a loose norm-wise bound."""
-    host, dev, oracle = make_pair("mini104", seed=4, exp_mode=1)
-    assert dev.sweep() == oracle.sweep()
-    assert np.array_equal(dev.get(api.ARR_QSR_DIGEST), oracle.digest)
-    err = rel_l2(dev.get(api.ARR_FINE_FLUX), oracle.fine_flux)
-    print(f"SFU vs expf oracle: fine_flux rel-L2 = {err:.3e}")
-    assert np.isfinite(err)
-    dev.close(); host.close(); oracle.close()
+@pytest.mark.parametrize("case", ["tiny", "mini104", "tiny_flat", "mini_default_in"])
+def test_sfu_mode_against_exact_exp_oracle(built, case):
+    """The SFU exponential (MUFU.EX2; the north star's performance mode) has no reference result to agree with
+    bit-wise: the reference's table is wrong-signed, so "exact exponential" is a different problem, and
+    in FP32 its formula cancels catastrophically (tau (tau (tau - 3) + 6) - 6 E for small tau): the reference's OWN
+    FP32 arithmetic with libm's expf is then 1e-3 .. 0.3 (rel-L2 of the scalar flux) away from the same formula
+    evaluated in double.  So the yardstick is that double evaluation (oracle exp_mode 2), and the bar is the
+    reference's own FP32 error against it (oracle exp_mode 1 == the reference built with 1 - expf(-x),
+    tests/test_oracle_vs_ref.py): the GPU may not be further from the truth than a small multiple of that.
+    Integers are exact as in every mode."""
+    host, dev, ref32 = make_pair(case, seed=4, exp_mode=1)
+    ref64 = OracleCase(CASES[case], seed=4, exp_mode=2)
+    n = dev.sweep()
+    assert n == ref32.sweep() == ref64.sweep()
+    assert np.array_equal(dev.get(api.ARR_SEG_COUNT), ref32.seg_count)
+    assert np.array_equal(dev.get(api.ARR_QSR_DIGEST), ref32.digest)
+    assert np.array_equal(dev.get(api.ARR_Z_HEIGHT), ref32.z_height)
+    flux, psi = dev.get(api.ARR_FINE_FLUX), dev.get(api.ARR_PSI)
+    truth_flux, truth_psi = ref64.flux64, ref64.psi64
+    e_gpu, e_ref = rel_l2(flux, truth_flux), rel_l2(ref32.fine_flux, truth_flux)
+    f_gpu, f_ref = frac_within(flux, truth_flux, TOL), frac_within(ref32.fine_flux, truth_flux, TOL)
+    p_gpu, p_ref = rel_l2(psi, truth_psi), rel_l2(ref32.psi, truth_psi)
+    med_gpu = float(np.median(np.abs(flux - truth_flux) / np.maximum(np.abs(truth_flux), 1e-300)))
+    med_ref = float(np.median(np.abs(ref32.fine_flux - truth_flux) / np.maximum(np.abs(truth_flux), 1e-300)))
+    print(f"SFU mode, {case}: scalar flux vs double: rel-L2 GPU {e_gpu:.3e} / reference FP32 {e_ref:.3e}; within 1e-4: "
+          f"{f_gpu:.5f} / {f_ref:.5f}; median relative error {med_gpu:.2e} / {med_ref:.2e}; angular flux rel-L2 "
+          f"{p_gpu:.3e} / {p_ref:.3e}; GPU vs reference FP32: rel-L2 {rel_l2(flux, ref32.fine_flux):.3e}")
+    assert e_gpu <= 4.0 * e_ref + 1e-6            # norm-wise: no further from the truth than 4x the reference itself
+    assert f_gpu >= f_ref - 0.02                  # element-wise: as many elements within 1e-4 of the truth (-2 %)
+    assert med_gpu <= 4.0 * med_ref + 1e-7        # the typical element
+    assert p_gpu <= 4.0 * p_ref + 1e-6 and p_gpu <= TOL    # the angular flux does not cancel: 1e-4 holds outright
+    dev.close(); host.close(); ref32.close(); ref64.close()
 
 
 @pytest.mark.parametrize("case", ["tiny", "mini104", "tall"])
@@ -287,7 +325,7 @@ def test_problem_from_an_openmoc_track_file(built, case):
         assert np.array_equal(d.get(api.ARR_SEG_COUNT), oracle.seg_count)
         assert np.array_equal(d.get(api.ARR_QSR_DIGEST), oracle.digest)
         assert np.array_equal(d.get(api.ARR_Z_HEIGHT), oracle.z_height)
-        check_state(d, oracle, f"{case} from a track file", noise_cap=256)
+        check_state(d, oracle, f"{case} from a track file", noise_cap=NOISE_CAP)
         d.renormalize(); oracle.renormalize()
         d.update_sources(1.0); oracle.update_sources(1.0)
         k_gpu, k_cpu = d.compute_keff(), oracle.compute_keff()

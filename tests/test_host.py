@@ -228,3 +228,36 @@ def test_build_tracks_matches_the_oracle_on_random_configurations(built):
             checked += 1
         host.close(); o.close()
     assert checked >= 60
+
+
+@pytest.mark.parametrize("case", ["tiny", "mini104", "tiny_flat", "tall", "ragged", "polar1"])
+def test_oracle_geometry_only_and_reversed_order_keep_every_integer(case):
+    """Two variants of the oracle's sweep used as yardsticks (never as the parity oracle itself):
+    geometry-only (oracle_create_geometry: what pins the FULL-SIZE problems' integers,
+    tests/golden/make_full_size_counts.py) and 2D tracks in reverse order (tools/tolerance_anchor.py: the same
+    tallies added in another order).  Both must reproduce the full oracle's segment counts, draws, digest and ray
+    heights bit for bit over two sweeps; the reversed order also its angular flux (only the scalar flux is order-
+    dependent)."""
+    from oracle_lib import CASES, OracleCase
+    seed = 2 if case in ("ragged", "polar1") else 3
+    full, geo, rev = (OracleCase(CASES[case], seed=seed), OracleCase(CASES[case], seed=seed, geometry_only=True),
+                      OracleCase(CASES[case], seed=seed))
+    assert full.init_rand_calls == geo.init_rand_calls
+    for sweep in range(2):
+        n = full.sweep()
+        assert geo.sweep() == n and rev.sweep_reversed() == n
+        for other in (geo, rev):
+            assert other.rand_calls == full.rand_calls
+            assert np.array_equal(other.seg_count, full.seg_count)
+            assert np.array_equal(other.digest, full.digest)
+            assert np.array_equal(other.z_height, full.z_height)
+        if sweep == 0:
+            assert np.array_equal(rev.psi, full.psi)
+            assert rel_l2_(rev.fine_flux, full.fine_flux) < 1e-5
+            rev.fine_flux[...] = full.fine_flux          # continue from identical tallies
+    full.close(); geo.close(); rev.close()
+
+
+def rel_l2_(a, b):
+    a, b = np.asarray(a, np.float64).ravel(), np.asarray(b, np.float64).ravel()
+    return float(np.linalg.norm(a - b) / np.linalg.norm(b))
