@@ -86,6 +86,10 @@ def parse_args():
                     help="--impl reference: sweep the WHOLE workload instead of a bounded sample (minutes per step; "
                          "the once-per-round check of the sampled figure, profiles/)")
     ap.add_argument("--no-full-loop", action="store_true", help="skip the e2e_full_loop leg")
+    ap.add_argument("--noclamp", type=int, default=1, choices=[0, 1],
+                    help="0: keep the table's x > maxVal test in every attenuation launch (A/B timing)")
+    ap.add_argument("--staged", type=int, default=1, choices=[0, 1],
+                    help="1 (default): TMA-staged attenuation kernel; 0: the direct-gather kernel (A/B timing)")
     return ap.parse_args()
 
 
@@ -471,6 +475,10 @@ def run_moc(args):
         host = m.HostProblem(inp, seed=1 + rank)          # every rank: a full-size domain of its own
         dev = m.DeviceProblem(host, device=local, exp_mode=exp_mode)
     build_s = time.time() - t0
+    if not args.staged:
+        dev.set_option(api.OPT_STAGED, 0)
+    if not args.noclamp:
+        dev.set_option(api.OPT_NOCLAMP, 0)
     cx, cy, cz = grid_for(world, args.grid)
     grid = m.make_grid(cx, cy, cz, rank)
     if world > 1:

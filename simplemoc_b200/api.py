@@ -81,6 +81,8 @@ OPT_FILL_OVERLAP, OPT_FILL_BATCHES = 9, 10
 OPT_DIGEST = 100
 OPT_EXACT_RAY_TRACE = 102
 OPT_FIT_PER_SEGMENT = 103   # diagnostic: quadratic fit per segment (the path of source slabs larger than the L2)
+OPT_NOCLAMP = 105           # set 0: keep the x > maxVal test of the table in every launch; get: 1 if the last sweep dropped it
+OPT_STAGED = 104            # 1 (default): TMA-staged attenuation kernel where it applies; 0: direct gathers (A/B timing)
 EXP_TABLE_REF, EXP_SFU = 0, 1
 ARR_FINE_SOURCE, ARR_FINE_FLUX, ARR_SIGT, ARR_PSI, ARR_Z_HEIGHT, ARR_P_WEIGHT, ARR_SEG_COUNT, ARR_QSR_DIGEST = \
     1, 2, 3, 4, 5, 6, 7, 8

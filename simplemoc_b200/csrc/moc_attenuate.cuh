@@ -17,6 +17,7 @@
  *     FMA-pipe cycle per warp instruction where a (half-empty) packed pair would take two.
  */
 #pragma once
+#include <type_traits>
 
 // MUFU.RCP / MUFU.EX2 without the range fix-ups of the libdevice wrappers
 __device__ __forceinline__ float rcp_approx(float x)
@@ -36,6 +37,24 @@ __device__ __forceinline__ float ex2_approx(float x)
 __device__ __forceinline__ float2 bc(float v) { return make_float2(v, v); }
 __device__ __forceinline__ float2 neg2(float2 a) { return make_float2(-a.x, -a.y); }
 __device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+// An FFMA2 whose three operands are all register PAIRS reads three even and three odd registers: alone it holds the
+// sub-partition's issue port for 3.06 cycles where two scalar FFMA take 2.2, and 2.05 with at most two register pairs
+// (tools/ubench/issue_slots.cu, profiles/r02_ubench_issue_slots.txt).  fma2r marks the seven such operations of a
+// pair of groups; MOC_UNPACK_RRR = 1 spells them as two FFMA (same roundings).  Measured in the kernel that is 2 %
+// SLOWER (356 vs 348 ms per launch on the default problem): mixed with the ALU-pipe instructions of the loop the
+// packed form's extra cycle is hidden, the extra issue slots of the scalar form are not.  Kept at 0.
+#ifndef MOC_UNPACK_RRR
+#define MOC_UNPACK_RRR 0
+#endif
+__device__ __forceinline__ float2 fma2r(float2 a, float2 b, float2 c)
+{
+#if MOC_UNPACK_RRR
+    return make_float2(__fmaf_rn(a.x, b.x, c.x), __fmaf_rn(a.y, b.y, c.y));
+#else
+    return __ffma2_rn(a, b, c);
+#endif
+}
+__device__ __forceinline__ float fma2r(float a, float b, float c) { return __fmaf_rn(a, b, c); }
 __device__ __forceinline__ float2 mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
 __device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
 __device__ __forceinline__ float2 sub2(float2 a, float2 b) { return __fadd2_rn(a, neg2(b)); }
@@ -102,14 +121,18 @@ struct SegmentScalars {
 //          is the reference's), IEEE division.
 //  MODE 1: the same with the verified fast division.
 //  MODE 2: SFU: MUFU.EX2.
-// All keep the reference's x > maxVal -> 1 rule (solver.c:1444-1445).
+//  MODE 3 / 4: MODE 1 / 2 without the reference's x > maxVal -> 1 rule (solver.c:1444-1445): for segments so short
+//  that no sigT of the slab can carry the optical length past maxVal (ds <= AttenuateParams::ds_noclamp, decided per
+//  segment and warp) the rule cannot fire and two instructions per group go.  (Not per sweep: in the last 2D segment
+//  of a track the reference measures the later 3D segments of a crossing ray from the ray's START height,
+//  solver.c:514-523 -- lengths up to node height / cos(polar), 22 cm on the default problem, 0.08 % of all segments.)
 template <int MODE>
 __device__ __forceinline__ void one_minus_exp2(float2 x, const TableConsts &tc, float2 &E, float2 &D)
 {
-    if (MODE == 2) {
+    if (MODE == 2 || MODE == 4) {
         const float2 arg = mul2(x, bc(-1.4426950408889634f));
-        D.x = x.x > tc.x_max ? 0.0f : ex2_approx(arg.x);
-        D.y = x.y > tc.x_max ? 0.0f : ex2_approx(arg.y);
+        D.x = (MODE == 2 && x.x > tc.x_max) ? 0.0f : ex2_approx(arg.x);
+        D.y = (MODE == 2 && x.y > tc.x_max) ? 0.0f : ex2_approx(arg.y);
         E = sub2(bc(1.0f), D);
     } else {
         float2 t;
@@ -123,8 +146,10 @@ __device__ __forceinline__ void one_minus_exp2(float2 x, const TableConsts &tc, 
             t = add2(q, bc(tc.half_dx));
         }
         int c0 = __float2int_rz(t.x), c1 = __float2int_rz(t.y);
-        c0 = x.x > tc.x_max ? tc.n : c0;
-        c1 = x.y > tc.x_max ? tc.n : c1;
+        if (MODE != 3) {
+            c0 = x.x > tc.x_max ? tc.n : c0;
+            c1 = x.y > tc.x_max ? tc.n : c1;
+        }
         // the halves of a packed operand come from different cells: one LDS.64 (slope, intercept) per group,
         // and the interpolation on two scalar FFMA (the same two FMA-pipe cycles as one FFMA2, without the
         // three register moves that re-pairing (slope0, slope1) / (intercept0, intercept1) costs)
@@ -140,8 +165,8 @@ __device__ __forceinline__ void one_minus_exp2(float2 x, const TableConsts &tc, 
 template <int MODE>
 __device__ __forceinline__ void one_minus_exp2(float x, const TableConsts &tc, float &E, float &D)
 {
-    if (MODE == 2) {
-        D = x > tc.x_max ? 0.0f : ex2_approx(__fmul_rn(x, -1.4426950408889634f));
+    if (MODE == 2 || MODE == 4) {
+        D = (MODE == 2 && x > tc.x_max) ? 0.0f : ex2_approx(__fmul_rn(x, -1.4426950408889634f));
         E = __fadd_rn(1.0f, -D);
     } else {
         float t;
@@ -154,7 +179,7 @@ __device__ __forceinline__ void one_minus_exp2(float x, const TableConsts &tc, f
             t = __fadd_rn(q, tc.half_dx);
         }
         int c = __float2int_rz(t);
-        c = x > tc.x_max ? tc.n : c;
+        if (MODE != 3) c = x > tc.x_max ? tc.n : c;
         const float2 e = *reinterpret_cast<const float2 *>(tc.tab + 2 * c);
         E = __fmaf_rn(e.x, x, e.y);
         D = __fadd_rn(1.0f, -E);
@@ -199,17 +224,17 @@ __device__ __forceinline__ V attenuate_groups(V c0, V d, V e, V sigT, V &psi, co
     const V r2 = mul2(r1, r1);
     const V Er1 = mul2(E, r1);
     const V reuse = fma2(splat<V>(2.f), mul2(Er1, r2), mul2(tau, add2(tau, splat<V>(-2.f))));
-    const V A = fma2(q0, tau, mul2(fma2(sigT, psi, neg2(q0)), E));
+    const V A = fma2r(q0, tau, mul2(fma2r(sigT, psi, neg2(q0)), E));
     const V c3 = fma2(splat<V>(-2.f), E,
                       mul2(tau, fma2(tau, fma2(tau, splat<V>(1.f / 3.f), splat<V>(-1.f)), splat<V>(2.f))));
-    const V X = fma2(mul2(q2m, r2), c3, A);
-    const V in = fma2(X, r2, mul2(q1m, reuse));
+    const V X = fma2r(mul2(q2m, r2), c3, A);
+    const V in = fma2r(X, r2, mul2(q1m, reuse));
     // psi (1 - E) with D = 1 - E formed first, as solver.c:264 does: folding it into (psi + out) - psi E
     // saves an instruction but moves the cancellation (measured: fewer elements within 1e-4 of the reference)
     V out = mul2(q0, Er1);
-    out = fma2(mul2(q1m, r2), sub2(tau, E), out);
-    out = fma2(q2m, reuse, out);
-    psi = fma2(psi, D, out);
+    out = fma2r(mul2(q1m, r2), sub2(tau, E), out);
+    out = fma2r(q2m, reuse, out);
+    psi = fma2r(psi, D, out);
     return mul2(splat<V>(k.weight), in);
 }
 
@@ -376,6 +401,7 @@ __global__ void __launch_bounds__(128, MOC_ATT_MIN_BLOCKS) attenuate_kernel(cons
         const float seg_ds = __shfl_sync(0xffffffffu, cur_ds, slot, L);
         const float zin = __shfl_sync(0xffffffffu, cur_zin, slot, L);
         const uint32_t code = __shfl_sync(0xffffffffu, cur_code, slot, L);
+        const bool need_clamp = __any_sync(0xffffffffu, sgm < n_rec && !(seg_ds <= a.ds_noclamp));
         if (sgm < n_rec) {
             sc.ds = seg_ds;
             sc.a1 = COEF ? zin : zin * a.inv_2dz;
@@ -391,50 +417,60 @@ __global__ void __launch_bounds__(128, MOC_ATT_MIN_BLOCKS) attenuate_kernel(cons
             const uint32_t o_src = COEF ? (qsr * a.coef_stencils + r0) * 3u * (uint32_t)W : o_row;
             const uint32_t o_sig = qsr * (uint32_t)W;
             const uint32_t o_flx = o_row + which * (uint32_t)W;
-#pragma unroll
-            for (int v = 0; v < NV4; v++) {
-                const int g = 4 * (lit + L * v);
-                if (g < G) {
-                    const float4 s4 = gather4(reinterpret_cast<const float4 *>(sig_q + o_sig + 4 * L * v));
-                    float4 tally;
-                    if (FLAT) {
-                        const float4 y = gather4(reinterpret_cast<const float4 *>(src_q + o_src + 4 * L * v));
-                        tally.x = attenuate_flat<MODE>(y.x, s4.x, psi4[v].x, sc, tc);
-                        tally.y = attenuate_flat<MODE>(y.y, s4.y, psi4[v].y, sc, tc);
-                        tally.z = attenuate_flat<MODE>(y.z, s4.z, psi4[v].z, sc, tc);
-                        tally.w = attenuate_flat<MODE>(y.w, s4.w, psi4[v].w, sc, tc);
-                    } else {
-                        const float4 k0 = gather4(reinterpret_cast<const float4 *>(src_q + o_src + 4 * L * v));
-                        const float4 k1 = gather4(reinterpret_cast<const float4 *>(src_q + o_src + W + 4 * L * v));
-                        const float4 k2 = gather4(reinterpret_cast<const float4 *>(src_q + o_src + 2 * W + 4 * L * v));
-                        float2 plo = make_float2(psi4[v].x, psi4[v].y), phi = make_float2(psi4[v].z, psi4[v].w);
-                        const float2 tlo = attenuate_groups<MODE, COEF>(
-                            make_float2(k0.x, k0.y), make_float2(k1.x, k1.y), make_float2(k2.x, k2.y),
-                            make_float2(s4.x, s4.y), plo, sc, tc);
-                        const float2 thi = attenuate_groups<MODE, COEF>(
-                            make_float2(k0.z, k0.w), make_float2(k1.z, k1.w), make_float2(k2.z, k2.w),
-                            make_float2(s4.z, s4.w), phi, sc, tc);
-                        psi4[v] = make_float4(plo.x, plo.y, phi.x, phi.y);
-                        tally = make_float4(tlo.x, tlo.y, thi.x, thi.y);
+            auto groups = [&](auto mode) {
+                constexpr int M = decltype(mode)::value;
+    #pragma unroll
+                for (int v = 0; v < NV4; v++) {
+                    const int g = 4 * (lit + L * v);
+                    if (g < G) {
+                        const float4 s4 = gather4(reinterpret_cast<const float4 *>(sig_q + o_sig + 4 * L * v));
+                        float4 tally;
+                        if (FLAT) {
+                            const float4 y = gather4(reinterpret_cast<const float4 *>(src_q + o_src + 4 * L * v));
+                            tally.x = attenuate_flat<M>(y.x, s4.x, psi4[v].x, sc, tc);
+                            tally.y = attenuate_flat<M>(y.y, s4.y, psi4[v].y, sc, tc);
+                            tally.z = attenuate_flat<M>(y.z, s4.z, psi4[v].z, sc, tc);
+                            tally.w = attenuate_flat<M>(y.w, s4.w, psi4[v].w, sc, tc);
+                        } else {
+                            const float4 k0 = gather4(reinterpret_cast<const float4 *>(src_q + o_src + 4 * L * v));
+                            const float4 k1 = gather4(reinterpret_cast<const float4 *>(src_q + o_src + W + 4 * L * v));
+                            const float4 k2 = gather4(reinterpret_cast<const float4 *>(src_q + o_src + 2 * W + 4 * L * v));
+                            float2 plo = make_float2(psi4[v].x, psi4[v].y), phi = make_float2(psi4[v].z, psi4[v].w);
+                            const float2 tlo = attenuate_groups<M, COEF>(
+                                make_float2(k0.x, k0.y), make_float2(k1.x, k1.y), make_float2(k2.x, k2.y),
+                                make_float2(s4.x, s4.y), plo, sc, tc);
+                            const float2 thi = attenuate_groups<M, COEF>(
+                                make_float2(k0.z, k0.w), make_float2(k1.z, k1.w), make_float2(k2.z, k2.w),
+                                make_float2(s4.z, s4.w), phi, sc, tc);
+                            psi4[v] = make_float4(plo.x, plo.y, phi.x, phi.y);
+                            tally = make_float4(tlo.x, tlo.y, thi.x, thi.y);
+                        }
+                        red_add_v4(flx_q + o_flx + 4 * L * v, tally);
                     }
-                    red_add_v4(flx_q + o_flx + 4 * L * v, tally);
                 }
-            }
-#pragma unroll
-            for (int s = 0; s < NS; s++) {
-                const int g = g_tail + lit + L * s;
-                if (g < G) {
-                    const float s1 = gather1(sig_s + o_sig + L * s);
-                    float tally;
-                    if (FLAT) {
-                        tally = attenuate_flat<MODE>(gather1(src_s + o_src + L * s), s1, psi1[s], sc, tc);
-                    } else {
-                        // the tail group runs on scalar FFMA/FMUL/FADD, not on a half-empty pair
-                        tally = attenuate_groups<MODE, COEF>(gather1(src_s + o_src + L * s), gather1(src_s + o_src + W + L * s),
-                                                       gather1(src_s + o_src + 2 * W + L * s), s1, psi1[s], sc, tc);
+    #pragma unroll
+                for (int s = 0; s < NS; s++) {
+                    const int g = g_tail + lit + L * s;
+                    if (g < G) {
+                        const float s1 = gather1(sig_s + o_sig + L * s);
+                        float tally;
+                        if (FLAT) {
+                            tally = attenuate_flat<M>(gather1(src_s + o_src + L * s), s1, psi1[s], sc, tc);
+                        } else {
+                            // the tail group runs on scalar FFMA/FMUL/FADD, not on a half-empty pair
+                            tally = attenuate_groups<M, COEF>(gather1(src_s + o_src + L * s), gather1(src_s + o_src + W + L * s),
+                                                           gather1(src_s + o_src + 2 * W + L * s), s1, psi1[s], sc, tc);
+                        }
+                        red_add(flx_s + o_flx + L * s, tally);
                     }
-                    red_add(flx_s + o_flx + L * s, tally);
                 }
+            };
+            // the x > maxVal test of the table only where a segment is long enough to need it (warp-uniform)
+            if constexpr (MODE == 0) {
+                groups(std::integral_constant<int, 0>());
+            } else {
+                if (need_clamp) groups(std::integral_constant<int, MODE>());
+                else groups(std::integral_constant<int, MODE + 2>());
             }
         }
     }
@@ -453,3 +489,304 @@ __global__ void __launch_bounds__(128, MOC_ATT_MIN_BLOCKS) attenuate_kernel(cons
     }
 }
 
+
+#ifndef MOC_ABLATE
+#define MOC_ABLATE 0   // experiments only: 1 = no operand copies, 2 = no reductions, 3 = neither (tools/gpu_runs)
+#endif
+
+// ------------------------------------------------------------------ K1 with the gathers staged by the TMA unit
+//
+// The same attenuation, lane mapping and arithmetic as attenuate_kernel (8 lanes per track, 4 tracks per warp, the
+// track's angular flux in registers); what changes is how the gathered rows reach the arithmetic.  There every lane
+// issues its own LDG.128 for (c0, c1, c2, sigT) of the segment at the top of the iteration and needs them at once:
+// ncu (profiles/r02_K1_baseline_ncu.txt) shows the FMA pipe 64 % busy and the L1TEX 66 % busy with 1.8 long-
+// scoreboard stalls per issue -- neither unit saturated, the two phases of a warp simply do not overlap, and 96
+// registers per thread leave only 5 warps per scheduler to cover for each other.  Here
+//   - fit_coefficients4_kernel packs (c0, c1, c2, sigT) of every (region, stencil) into ONE contiguous block of
+//     16 G bytes (G = 104: 1664 B = 13 full 128-byte lines, no padding): one segment of one track needs one block;
+//   - every warp owns a two-stage ring in shared memory; the leader lane of each track issues ONE bulk copy
+//     (cp.async.bulk global -> shared, SASS UBLKCP, completion counted on an mbarrier) for the segment two steps
+//     ahead as soon as the stage is free, so a block has a whole segment's arithmetic (~2000 cycles) to arrive;
+//   - the arithmetic reads its operands with LDS.128 at immediate offsets: no address arithmetic, no long
+//     scoreboard, fewer live registers.
+// L2 -> SM traffic per integration is unchanged (16 B + the 4-byte reduction); the copies bypass the LSU's tag
+// stage and miss handling.
+struct StagedParams {
+    AttenuateParams a;
+    const float *coef4;      // [N][stencils][4][G]  (c0 | c1 | c2 | sigT), rows of exactly G floats
+};
+
+// coef4[i][r0][0..2][G] = the fit of source rows r0 .. r0+2 as solver.c:74-76 writes it, [3][G] = sigT of region i
+__global__ void fit_coefficients4_kernel(const float *__restrict__ fine_source, const float *__restrict__ sigT,
+                                         float *__restrict__ coef4, long long n_regions, int fai, int pitch, int G, float dz)
+{
+    const int S = fai - 2;
+    const long long cells = n_regions * S * G;
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= cells) return;
+    const int g = (int)(e % G);
+    const long long rs = e / G;
+    const int r0 = (int)(rs % S);
+    const long long i = rs / S;
+    const float *y = fine_source + ((size_t)i * fai + r0) * pitch + g;
+    const float y1 = y[0], y2 = y[pitch], y3 = y[2 * pitch];
+    float *c = coef4 + (size_t)rs * 4 * G + g;
+    const float two_dz = __fmul_rn(2.f, dz);
+    c[0] = y2;
+    c[G] = __fdiv_rn(__fadd_rn(y1, -y3), two_dz);
+    c[2 * G] = __fdiv_rn(__fadd_rn(__fadd_rn(y1, -__fmul_rn(2.f, y2)), y3), __fmul_rn(two_dz, dz));
+    c[3 * G] = sigT[(size_t)i * pitch + g];
+}
+
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t done;
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    return done != 0;
+}
+// global -> shared bulk copy by the TMA unit; `bytes` (a multiple of 16) are counted on the mbarrier when they land
+__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+// shared-memory plan of attenuate_staged_kernel for G groups (host and device agree through these)
+__host__ __device__ constexpr int staged_track_stride(int G)
+{
+    // 16 G bytes per block; padded so that consecutive tracks start 32 bytes further along the banks (stride = 32
+    // mod 128): the four tracks' tail groups (8 lanes x 4 bytes each) then hit four different bank octets
+    return 16 * G + ((32 - (16 * G) % 128) + 128) % 128;
+}
+__host__ __device__ constexpr int staged_table_bytes(int table_n) { return (8 * (table_n + 1) + 127) / 128 * 128; }
+__host__ __device__ constexpr int staged_smem_bytes(int G, int table_n, int warps, bool table)
+{
+    return (table ? staged_table_bytes(table_n) : 0) + 128 /* mbarriers */ + warps * 2 * 4 * staged_track_stride(G);
+}
+
+template <int NV4, int NS, int MODE, int GC>
+__global__ void __launch_bounds__(128, 4) attenuate_staged_kernel(const StagedParams sp)
+{
+    const AttenuateParams &a = sp.a;
+    constexpr int L = 8, TPW = 4, G = GC;
+    constexpr int STRIDE = staged_track_stride(G), STAGE = TPW * STRIDE, BLOCK_BYTES = 16 * G;
+    extern __shared__ __align__(128) unsigned char s_raw[];
+    constexpr bool TABLE = MODE != 2;
+    const int table_bytes = TABLE ? staged_table_bytes(a.table_n) : 0;
+    float *s_tab = reinterpret_cast<float *>(s_raw);
+    TableConsts tc;
+    tc.dx = a.table_dx; tc.rdx = a.table_rdx; tc.half_dx = a.table_half_dx; tc.x_max = a.table_max;
+    tc.n = a.table_n;
+    tc.tab = s_tab;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lit = lane % L, grp = lane / L;
+    const uint32_t bars = smem_addr(s_raw + table_bytes) + 16u * warp;             // two mbarriers per warp
+    unsigned char *const ring = s_raw + table_bytes + 128 + (size_t)warp * 2 * STAGE;
+    if (TABLE) {
+        for (int e = threadIdx.x; e < 2 * a.table_n; e += blockDim.x) s_tab[e] = a.table[e];
+        if (threadIdx.x == 0) {
+            s_tab[2 * a.table_n] = 0.f;
+            s_tab[2 * a.table_n + 1] = 1.f;
+        }
+    }
+#if MOC_ABLATE & 1
+    for (int e = lane; e < 2 * STAGE / 4; e += 32) reinterpret_cast<float *>(ring)[e] = 0.5f;
+#endif
+    if (lane == 0) {
+        mbar_init(bars, TPW);          // one arrival per track leader and use of the stage
+        mbar_init(bars + 8, TPW);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const long long t = a.first_track + ((long long)blockIdx.x * (blockDim.x >> 5) + warp) * TPW + grp;
+    const bool valid = t < a.end_track;
+    uint32_t n_rec = 0, at = 0;
+    SegmentScalars sc;
+    sc.ds = 0.f; sc.a1 = sc.a2 = sc.b1 = sc.b2 = sc.b3 = 0.f; sc.weight = 0.f;
+    float mu = 0.f;
+    if (valid) {
+        n_rec = a.seg_count[t];
+        const long long pair = t / a.Z;
+        at = (uint32_t)(a.rec_base[pair] - a.batch_first_record) + (uint32_t)(t - pair * a.Z);
+        const int j = (int)(pair % a.P);
+        const long long i = pair / a.P;
+        mu = a.mu[j];
+        sc.weight = __fmul_rn(a.p_weight[t], a.az_weight[i]);   // solver.c:49
+        sc.b1 = mu;
+        sc.b3 = mu * mu;
+    }
+    const float two_mu = 2.f * mu;
+    unsigned int longest = n_rec;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        unsigned int o = __shfl_xor_sync(0xffffffffu, longest, d);
+        longest = o > longest ? o : longest;
+    }
+
+    constexpr int g_tail = 4 * L * NV4;
+    float4 psi4[NV4 > 0 ? NV4 : 1];
+    float psi1[NS > 0 ? NS : 1];
+    float *psi_row = a.psi + (size_t)2 * (size_t)(valid ? t : 0) * G;
+#pragma unroll
+    for (int v = 0; v < NV4; v++) {
+        const int g = 4 * (lit + L * v);
+        psi4[v] = (valid && g < G) ? *reinterpret_cast<const float4 *>(psi_row + g) : make_float4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int s = 0; s < NS; s++) {
+        const int g = g_tail + lit + L * s;
+        psi1[s] = (valid && g < G) ? psi_row[g] : 0.f;
+    }
+
+    // segment records, eight at a time, one block ahead (as in attenuate_kernel)
+    const float *rec_ds = a.rec_ds + at;
+    const float *rec_zin = a.rec_zin + at;
+    const uint32_t *rec_code = a.rec_code + at;
+    float cur_ds = 0.f, cur_zin = 0.f, nxt_ds = 0.f, nxt_zin = 0.f;
+    uint32_t cur_code = 0, nxt_code = 0;
+    const uint32_t Zs = (uint32_t)a.Zs;
+    if ((uint32_t)lit < n_rec) {
+        nxt_ds = __ldg(rec_ds + lit * Zs);
+        nxt_zin = __ldg(rec_zin + lit * Zs);
+        nxt_code = __ldg(rec_code + lit * Zs);
+    }
+    const uint32_t stencils = (uint32_t)a.coef_stencils;
+    // the leader lane of a track asks the TMA unit for the coefficient block of one of its segments
+    auto request = [&](uint32_t code, bool active, int stage) {
+#if MOC_ABLATE & 1      // experiment: no copies (operands stay whatever the ring was filled with)
+        return;
+#endif
+        if (lit == 0) {
+            const uint32_t bar = bars + 8u * stage;
+            if (active) {
+                const uint32_t qsr = code & 0xffffffu, r0 = (code >> 24) & 63u;
+                const float *src = sp.coef4 + (size_t)(qsr * stencils + r0) * (size_t)(4 * G);
+                mbar_arrive_expect_tx(bar, BLOCK_BYTES);
+                bulk_copy_g2s(smem_addr(ring + stage * STAGE + grp * STRIDE), src, BLOCK_BYTES, bar);
+            } else {
+                mbar_arrive(bar);
+            }
+        }
+    };
+    // segments 0 and 1 (block 0 of the records still sits in nxt_*)
+    {
+        const uint32_t c0 = __shfl_sync(0xffffffffu, nxt_code, 0, L), c1 = __shfl_sync(0xffffffffu, nxt_code, 1, L);
+        if (longest > 0) request(c0, 0 < n_rec, 0);
+        if (longest > 1) request(c1, 1 < n_rec, 1);
+    }
+    float *const flx_q = a.fine_flux + 4 * lit;
+    float *const flx_s = a.fine_flux + g_tail + lit;
+
+    for (unsigned int sgm = 0; sgm < longest; sgm++) {
+        const int slot = sgm % L, stage = sgm & 1;
+        if (slot == 0) {
+            cur_ds = nxt_ds; cur_zin = nxt_zin; cur_code = nxt_code;
+            const uint32_t ahead = sgm + L + lit;
+            if (ahead < n_rec) {
+                nxt_ds = __ldg(rec_ds + ahead * Zs);
+                nxt_zin = __ldg(rec_zin + ahead * Zs);
+                nxt_code = __ldg(rec_code + ahead * Zs);
+            }
+        }
+        const float seg_ds = __shfl_sync(0xffffffffu, cur_ds, slot, L);
+        const float zin = __shfl_sync(0xffffffffu, cur_zin, slot, L);
+        const uint32_t code = __shfl_sync(0xffffffffu, cur_code, slot, L);
+        // the record of the segment two steps ahead: in this block of eight, or already in the next one
+        const uint32_t code2 = __shfl_sync(0xffffffffu, slot < L - 2 ? cur_code : nxt_code, (slot + 2) % L, L);
+        const bool need_clamp = __any_sync(0xffffffffu, sgm < n_rec && !(seg_ds <= a.ds_noclamp));
+#if !(MOC_ABLATE & 1)
+        while (!mbar_try_wait(bars + 8u * stage, (sgm >> 1) & 1u)) { }
+#endif
+        if (sgm < n_rec) {
+            sc.ds = seg_ds;
+            sc.a1 = zin;
+            sc.a2 = zin * zin;
+            sc.b2 = two_mu * zin;
+            const uint32_t qsr = code & 0xffffffu;
+            const uint32_t r0 = (code >> 24) & 63u;
+            const uint32_t which = code >> 30;
+            const uint32_t o_flx = (qsr * a.fai + r0 + which) * (uint32_t)a.pitch;
+            const unsigned char *blk = ring + stage * STAGE + grp * STRIDE;
+            const float *rows = reinterpret_cast<const float *>(blk);
+            auto groups = [&](auto mode) {
+                constexpr int M = decltype(mode)::value;
+    #pragma unroll
+                for (int v = 0; v < NV4; v++) {
+                    const int g = 4 * (lit + L * v);
+                    if (g < G) {
+                        const float4 k0 = *reinterpret_cast<const float4 *>(rows + g);
+                        const float4 k1 = *reinterpret_cast<const float4 *>(rows + G + g);
+                        const float4 k2 = *reinterpret_cast<const float4 *>(rows + 2 * G + g);
+                        const float4 s4 = *reinterpret_cast<const float4 *>(rows + 3 * G + g);
+                        float2 plo = make_float2(psi4[v].x, psi4[v].y), phi = make_float2(psi4[v].z, psi4[v].w);
+                        const float2 tlo = attenuate_groups<M, true>(
+                            make_float2(k0.x, k0.y), make_float2(k1.x, k1.y), make_float2(k2.x, k2.y),
+                            make_float2(s4.x, s4.y), plo, sc, tc);
+                        const float2 thi = attenuate_groups<M, true>(
+                            make_float2(k0.z, k0.w), make_float2(k1.z, k1.w), make_float2(k2.z, k2.w),
+                            make_float2(s4.z, s4.w), phi, sc, tc);
+                        psi4[v] = make_float4(plo.x, plo.y, phi.x, phi.y);
+    #if MOC_ABLATE & 2      // experiment: no reductions (the tallies are folded into psi so the arithmetic stays live)
+                        psi4[v].x += 1e-30f * (tlo.x + tlo.y + thi.x + thi.y);
+    #else
+                        red_add_v4(flx_q + o_flx + 4 * L * v, make_float4(tlo.x, tlo.y, thi.x, thi.y));
+    #endif
+                    }
+                }
+    #pragma unroll
+                for (int s = 0; s < NS; s++) {
+                    const int g = g_tail + lit + L * s;
+                    if (g < G) {
+                        const float tally = attenuate_groups<M, true>(rows[g], rows[G + g], rows[2 * G + g], rows[3 * G + g],
+                                                                         psi1[s], sc, tc);
+    #if MOC_ABLATE & 2
+                        psi1[s] += 1e-30f * tally;
+    #else
+                        red_add(flx_s + o_flx + L * s, tally);
+    #endif
+                    }
+                }
+            };
+            if constexpr (MODE == 0) {
+                groups(std::integral_constant<int, 0>());
+            } else {
+                if (need_clamp) groups(std::integral_constant<int, MODE>());
+                else groups(std::integral_constant<int, MODE + 2>());
+            }
+        }
+        // Every lane has consumed its operands of this stage (the reductions above depend on them): hand the stage
+        // to the copy of segment sgm + 2.  Write-after-read across the generic and the async proxy needs no proxy
+        // fence (that is for generic WRITES the async proxy reads); the warp barrier orders the lanes' reads before
+        // the leaders' requests, as the consumer-release / producer-acquire pair of a TMA pipeline does.
+        __syncwarp();
+        if (sgm + 2 < longest) request(code2, sgm + 2 < n_rec, stage);
+    }
+
+    if (valid) {
+#pragma unroll
+        for (int v = 0; v < NV4; v++) {
+            const int g = 4 * (lit + L * v);
+            if (g < G) *reinterpret_cast<float4 *>(psi_row + g) = psi4[v];
+        }
+#pragma unroll
+        for (int s = 0; s < NS; s++) {
+            const int g = g_tail + lit + L * s;
+            if (g < G) psi_row[g] = psi1[s];
+        }
+    }
+}

@@ -107,6 +107,7 @@ struct DeviceBuffers {
     // sources
     float *src = nullptr, *xs = nullptr, *scatter = nullptr, *vol = nullptr, *table = nullptr;
     float *coef = nullptr;               // quadratic fit coefficients of every stencil, rebuilt before each sweep
+    float *coef4 = nullptr;              // the same + sigT packed per (region, stencil) for the TMA-staged attenuation
     int *xs_index = nullptr;
     // sweep scratch
     uint32_t *seg_count = nullptr, *pair_max = nullptr, *rec_code = nullptr;
@@ -154,6 +155,14 @@ struct moc_handle {
     int fill_overlap_ctas = 0;
     int fill_batches = 8;          // batches per chunk of z-stacks when the two overlap
     int fit_per_segment = 0;       // diagnostic: 1 = never use the coefficient slab
+    int staged = 1;                // 1 (default): TMA-staged attenuation where it applies, 0: direct gathers
+    int allow_noclamp = 1;         // 0: always keep the x > maxVal test of the table (A/B timing, option 105)
+    bool sigT_known = false;       // sigT_max / sigT_clean describe the slab on the device
+    float sigT_max = 0.f;
+    bool sigT_clean = false;
+    double min_abs_sin = 0.0, min_abs_cos = 0.0;   // over the polar angles
+    mutable bool noclamp_now = false;   // this sweep's attenuation launches skip the x > maxVal test
+    mutable bool staged_now = false;   // what the current sweep uses
     cudaStream_t fill_stream = nullptr;
     int n_sm = 0;
     int want_digest = 0;
@@ -202,7 +211,7 @@ static int dev_alloc(T **p, size_t count)
 static void free_buffers(DeviceBuffers &d)
 {
     void *all[] = {d.az_weight, d.n_seg, d.seg_start, d.seg_len, d.cos_p, d.sin_p, d.mu, d.p_weight,
-                   d.z_height, d.psi, d.track_image, d.src, d.coef, d.xs, d.scatter, d.vol, d.table,
+                   d.z_height, d.psi, d.track_image, d.src, d.coef, d.coef4, d.xs, d.scatter, d.vol, d.table,
                    d.xs_index, d.seg_count, d.pair_max, d.rec_code, d.pair_count, d.pair_base, d.rec_base,
                    d.digest, d.rec_ds, d.rec_zin, d.per_region_a, d.per_region_b, d.per_fine,
                    d.scalars, d.leakage};
@@ -217,6 +226,7 @@ static void free_buffers(DeviceBuffers &d)
 // rows [row0, row0 + rows) of the slab <-> a dense host array of G-float rows.
 static cudaError_t slab_to_device(moc_handle *h, size_t row0, size_t rows, const float *host)
 {
+    if (row0 + rows > (size_t)2 * h->N * h->F) h->sigT_known = false;   // the copy reaches the sigT rows
     return cudaMemcpy2DAsync(h->d.src + row0 * h->Gp, sizeof(float) * h->Gp, host, sizeof(float) * h->G,
                              sizeof(float) * h->G, rows, cudaMemcpyHostToDevice, h->stream);
 }
@@ -346,6 +356,11 @@ static int upload_static(moc_handle *h, const Params *P, const HostLayout &L, bo
         c[(size_t)j] = cos((double)ang);
         s[(size_t)j] = sin((double)ang);
         mu[(size_t)j] = (float)cos((double)ang);
+    }
+    h->min_abs_sin = h->min_abs_cos = Pn > 0 ? 1.0 : 0.0;
+    for (int j = 0; j < Pn; j++) {
+        h->min_abs_sin = std::min(h->min_abs_sin, fabs(s[(size_t)j]));
+        h->min_abs_cos = std::min(h->min_abs_cos, fabs(c[(size_t)j]));
     }
     if ((rc = dev_alloc(&h->d.cos_p, (size_t)Pn))) return rc;
     if ((rc = dev_alloc(&h->d.sin_p, (size_t)Pn))) return rc;
@@ -617,7 +632,7 @@ static int create_common(const Input *I, const Params *P, int device, int source
     if ((rc = dev_alloc(&h->d.pair_base, pairs + 1))) return fail(rc);
     if ((rc = dev_alloc(&h->d.rec_base, pairs + 1))) return fail(rc);
     if ((rc = dev_alloc(&h->d.pair_max, pairs))) return fail(rc);
-    if ((rc = dev_alloc(&h->d.digest, 5))) return fail(rc);   // [4]: ray-trace flags
+    if ((rc = dev_alloc(&h->d.digest, 8))) return fail(rc);   // [4]: ray-trace flags, [5]: sigT range (sweep_core)
     if ((rc = dev_alloc(&h->d.per_region_a, N))) return fail(rc);
     if ((rc = dev_alloc(&h->d.per_region_b, N))) return fail(rc);
     if ((rc = dev_alloc(&h->d.per_fine, N * F))) return fail(rc);
@@ -628,7 +643,7 @@ static int create_common(const Input *I, const Params *P, int device, int source
         return fail(MOC_ENOMEM);
     }
     cudaMemsetAsync(h->d.seg_count, 0, sizeof(uint32_t) * T3, h->stream);
-    cudaMemsetAsync(h->d.digest, 0, sizeof(unsigned long long) * 5, h->stream);
+    cudaMemsetAsync(h->d.digest, 0, sizeof(unsigned long long) * 8, h->stream);
     cudaMemsetAsync(h->d.scalars, 0, sizeof(float) * 8, h->stream);
     h->leakage_host = P->leakage ? *P->leakage : 0.f;
     cudaMemcpyAsync(h->d.leakage, &h->leakage_host, sizeof(float), cudaMemcpyHostToDevice, h->stream);
@@ -737,6 +752,8 @@ extern "C" int moc_set_option(moc_handle *h, int option, long value)
         h->fill_batches = (int)value;
         return MOC_OK;
     case 103: h->fit_per_segment = value != 0; return MOC_OK;   // diagnostic: quadratic fit per segment (large-slab path)
+    case 104: h->staged = value != 0; return MOC_OK;            // 0 = attenuation with direct gathers (A/B timing)
+    case 105: h->allow_noclamp = value != 0; return MOC_OK;     // 0 = keep the x > maxVal test in every launch (A/B timing)
     case 100: h->want_digest = value != 0; return MOC_OK;   // MOC_OPT_DIGEST (diagnostic)
     case 102:                                                // diagnostic: 1 = ray trace with IEEE divisions / hardware remainders only
         if (value) h->iv_fast = h->fine_fast = h->mod_fast = 0;
@@ -764,6 +781,8 @@ extern "C" long moc_get_option(moc_handle *h, int option)
     case MOC_OPT_FILL_OVERLAP: return h->fill_overlap_ctas;
     case MOC_OPT_FILL_BATCHES: return h->fill_batches;
     case 103: return h->fit_per_segment || !h->d.coef;
+    case 104: return h->staged;
+    case 105: return h->noclamp_now;
     case 100: return h->want_digest;
     case 101: return !h->fast_cell_ok;
     case 102: return !(h->iv_fast && h->fine_fast && h->mod_fast);

@@ -100,6 +100,8 @@ struct AttenuateParams {
     long long first_track, end_track; // tracks of this batch
     int P, Z, G, fai;
     float inv_2dz, inv_2dz2;          // 1/(2 dz), 1/(2 dz dz) of solver.c:75-76 (only when the fit is done per segment)
+    float ds_noclamp;                 // segments no longer than this cannot reach the end of the exponential table with
+                                      // any sigT of the slab (0: unknown, every segment keeps the x > maxVal test)
 };
 
 // record code: | which:2 | r0:6 | qsr:24 |   (stencil rows r0..r0+2, tally row r0+which)
@@ -745,6 +747,28 @@ __global__ void patch_tracks_kernel(TrackImage *img, long long n, const float *z
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
     img[t].z_height = z_height[t];
+}
+
+// Largest total cross section of the slab (and whether every value is a finite, non-negative number): what the host
+// needs to prove that no optical length sigT x ds of a sweep reaches the end of the exponential table, so that the
+// attenuation may drop the reference's x > maxVal test (moc_attenuate.cuh, MODE 3 / 4).
+// out[0]: bits of the maximum (non-negative floats order like their bit patterns), out[1]: number of bad values.
+__global__ void sigt_range_kernel(const float *sigT, long long n_regions, int G, int pitch, unsigned int *out)
+{
+    const long long cells = n_regions * G;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    unsigned int mx = 0, bad = 0;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < cells; e += stride) {
+        const float v = sigT[(e / G) * pitch + (e % G)];
+        if (!(v >= 0.0f) || v > 3.0e38f) bad++;
+        else mx = max(mx, __float_as_uint(v));
+    }
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    bad = __reduce_add_sync(0xffffffffu, bad);
+    if ((threadIdx.x & 31) == 0) {
+        atomicMax(out, mx);
+        if (bad) atomicAdd(out + 1, bad);
+    }
 }
 
 // ------------------------------------------------------------------ synthetic problem

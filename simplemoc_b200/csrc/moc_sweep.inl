@@ -193,9 +193,66 @@ static int launch_attenuate_mode(const moc_handle *h, const AttenuateParams &a, 
     return MOC_OK;
 }
 
+// Does the TMA-staged attenuation kernel apply to this problem?  Quadratic source with the per-stencil coefficient
+// slab (L2-resident working set), one of the group counts it is instantiated for, default lane mapping, and a
+// shared-memory plan (table + two-stage ring per warp) that fits an SM.
+static bool staged_applies(const moc_handle *h)
+{
+    if (!h->staged || h->I.axial_exp != 2 || !h->d.coef || h->fit_per_segment || h->lanes_override) return false;
+    const int G = h->G;
+    if (G != 104 && G != 100 && G != 128 && G != 64 && G != 32) return false;
+    if ((double)h->N * (h->F - 2) * 4.0 * G >= 4294967296.0) return false;
+    return staged_smem_bytes(G, h->table_n, 4, h->exp_mode != 1) <= 227 * 1024;
+}
+
+template <int NV4, int NS, int GC>
+static int launch_staged_mode(const moc_handle *h, const StagedParams &sp, unsigned grid)
+{
+    const int mode = h->exp_mode == 1 ? 2 : (h->fast_cell_ok ? 1 : 0);
+    const int smem = staged_smem_bytes(GC, h->table_n, 4, mode != 2);
+    h->launch_count++;
+#define MOC_LAUNCH_STAGED(M)                                                                                        \
+    do {                                                                                                           \
+        static int smem_allowed = 0;                                                                               \
+        if (smem > smem_allowed) {                                                                                 \
+            if (cudaFuncSetAttribute(attenuate_staged_kernel<NV4, NS, M, GC>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                     smem) != cudaSuccess) {                                                       \
+                moc_set_error("attenuate_staged_kernel: %d bytes of shared memory refused", smem);                 \
+                cudaGetLastError();                                                                                \
+                return MOC_ECUDA;                                                                                  \
+            }                                                                                                      \
+            smem_allowed = smem;                                                                                   \
+        }                                                                                                          \
+        attenuate_staged_kernel<NV4, NS, M, GC><<<grid, 128, smem, h->stream>>>(sp);                               \
+    } while (0)
+    if (mode == 0) MOC_LAUNCH_STAGED(0);
+    else if (mode == 1) MOC_LAUNCH_STAGED(1);
+    else MOC_LAUNCH_STAGED(2);
+#undef MOC_LAUNCH_STAGED
+    return MOC_OK;
+}
+
+static int launch_staged(const moc_handle *h, const AttenuateParams &a, long long n_tracks)
+{
+    StagedParams sp;
+    sp.a = a;
+    sp.coef4 = h->d.coef4;
+    const unsigned grid = (unsigned)((n_tracks + 15) / 16);
+    switch (h->G) {
+    case 104: return launch_staged_mode<3, 1, 104>(h, sp, grid);
+    case 100: return launch_staged_mode<3, 1, 100>(h, sp, grid);
+    case 128: return launch_staged_mode<4, 0, 128>(h, sp, grid);
+    case 64: return launch_staged_mode<2, 0, 64>(h, sp, grid);
+    case 32: return launch_staged_mode<1, 0, 32>(h, sp, grid);
+    }
+    moc_set_error("no staged attenuation kernel for %d groups", h->G);
+    return MOC_EINVAL;
+}
+
 static int launch_attenuate(const moc_handle *h, const AttenuateParams &a, long long n_tracks)
 {
     if (n_tracks <= 0) return MOC_OK;
+    if (h->staged_now) return launch_staged(h, a, n_tracks);
     const LaneMap m = choose_lanes(h->G, h->lanes_override);
     if (4 * m.L * m.NV4 + m.L * m.NS < h->G) {
         moc_set_error("no lane mapping for %d energy groups", h->G);
@@ -472,8 +529,37 @@ static int sweep_core(moc_handle *h, long *segments_processed, const HostLayout 
     a.G = h->G;
     a.fai = h->F;
 
-    if (a.coef) {
-        // the source only changes between sweeps (update_sources, uploads): fit every stencil once
+    // Which segments may skip the reference's x > maxVal test of the table (solver.c:1444-1445)?  Those whose optical
+    // length cannot get there with ANY cross section of the slab: ds <= 0.99 maxVal / (largest sigT).  The largest sigT
+    // is found once per upload of the slab (resident problems: once); a slab with a negative or non-finite value, or one
+    // the host streams in with every call, keeps the test everywhere.
+    a.ds_noclamp = 0.f;
+    if (!io && h->allow_noclamp) {
+        if (!h->sigT_known) {
+            unsigned int *out = reinterpret_cast<unsigned int *>(h->d.digest + 5), host_out[2] = {0, 1};
+            CUDA_TRY(cudaMemsetAsync(out, 0, 2 * sizeof(unsigned int), h->stream));
+            sigt_range_kernel<<<148 * 4, 256, 0, h->stream>>>(a.sigT, h->N, h->G, h->Gp, out);
+            h->launch_count++;
+            CUDA_TRY(cudaMemcpyAsync(host_out, out, sizeof host_out, cudaMemcpyDeviceToHost, h->stream));
+            CUDA_TRY(cudaStreamSynchronize(h->stream));
+            memcpy(&h->sigT_max, &host_out[0], sizeof(float));
+            h->sigT_clean = host_out[1] == 0;
+            h->sigT_known = true;
+        }
+        if (h->sigT_clean && h->table_max > 0.f)
+            a.ds_noclamp = h->sigT_max > 0.f ? (float)(0.99 * (double)h->table_max / (double)h->sigT_max) : 3.0e38f;
+    }
+    h->noclamp_now = a.ds_noclamp > 0.f;
+    h->staged_now = staged_applies(h);
+    if (h->staged_now && !h->d.coef4 && (rc = dev_alloc(&h->d.coef4, (size_t)h->N * (h->F - 2) * 4 * (size_t)h->G))) return rc;
+    if (h->staged_now) {
+        // the source only changes between sweeps (update_sources, uploads): fit every stencil once, and pack
+        // (c0, c1, c2, sigT) of a stencil into one contiguous block for the bulk copies of the staged kernel
+        const long long cells = h->N * (h->F - 2) * (long long)h->G;
+        fit_coefficients4_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, h->stream>>>(
+            h->d.src, a.sigT, h->d.coef4, h->N, h->F, h->Gp, h->G, w.dz_fine);
+        h->launch_count++;
+    } else if (a.coef) {
         const long long cells = h->N * (h->F - 2) * (long long)h->Gp;
         fit_coefficients_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, h->stream>>>(
             h->d.src, h->d.coef, h->N, h->F, h->Gp, w.dz_fine);
