@@ -336,6 +336,11 @@ def run_reference(args):
 # cycles per warp instruction, scalar FFMA/FMUL/FADD/IMAD for one); ncu's sm__pipe_fma_cycles_active of the same
 # launch is the cross-check (profiles/).  Keep in step with moc_attenuate.cuh.
 K1_PIPE_MIX = {"table": (210, 60), "sfu": (192, 45)}     # (packed, scalar) per segment and lane
+# ... and the instructions it issues per segment and lane (loop body of the staged kernel, table mode 437 with the
+# per-segment skip of the x > maxVal test, SFU mode 385); a packed FP32x2 instruction holds the issue port of its
+# sub-partition for a second cycle (tools/ubench/issue_slots.cu: 2.04 cycles): issue cycles = instructions + packed.
+# The arithmetic alone, operands already in shared memory, runs AT this limit (profiles/r02_K1_findings.md).
+K1_ISSUED = {"table": 437, "sfu": 385}
 
 
 def k1_roofline(args, api, dev_opts, inp, state, step_ms_total, clocks, l2_probe, torch, local, world):
@@ -423,6 +428,11 @@ def k1_roofline(args, api, dev_opts, inp, state, step_ms_total, clocks, l2_probe
         exact = G == 104 and inp.axial_exp == 2
         peak = n_sm * 128 * sm_mhz * 1e6 * 2 / 1e12          # TFLOP/s the FMA pipes can issue at this clock
         achieved = my_integ * cycles * 2 / att_s / 1e12 if att_s else None
+        issue_cycles = (K1_ISSUED[args.exp] + packed) / 13.0
+        roof["issue"] = {"issue_cycles_per_integration": issue_cycles,
+                         "frac_of_issue_slots": my_integ * issue_cycles / att_s / (n_sm * 4 * 32 * sm_mhz * 1e6) if att_s else None,
+                         "note": "instructions issued + one extra cycle per packed FP32x2 instruction, against 4 sub-partitions x "
+                                 "1 warp-instruction (32 lanes) per cycle: what the loop is actually bound by"}
         roof.update({"bound": "fp32", "unit": "TFLOP/s", "achieved": achieved, "peak": peak,
                      "peak_source": f"{n_sm} SMs x 128 FP32 lanes x 2 FLOP x {sm_mhz:.0f} MHz (SM clock sampled during the run)",
                      "fma_pipe_lane_cycles_per_integration": cycles,
@@ -491,7 +501,7 @@ def run_moc(args):
 
     stream = torch.cuda.ExternalStream(dev.stream, device=torch.device("cuda", local))
     G = inp.n_egroups
-    state = {"keff": 1.0, "segments": 0, "att_ms": 0.0, "fill_ms": 0.0, "count_ms": 0.0, "sweep_ms": 0.0}
+    state = {"keff": 1.0, "segments": 0, "att_ms": 0.0, "fill_ms": 0.0, "count_ms": 0.0, "scan_ms": 0.0, "sweep_ms": 0.0}
 
     def step(accumulate):
         # N > 1: the exchange runs under the sweep of the interior z-stacks (moc_sweep_exchange)
@@ -510,6 +520,7 @@ def run_moc(args):
             state["att_ms"] += t.attenuate_ms
             state["fill_ms"] += t.fill_ms
             state["count_ms"] += t.count_ms
+            state["scan_ms"] += t.scan_ms
             state["sweep_ms"] += t.total_ms
         return n
 
@@ -614,8 +625,8 @@ def run_moc(args):
                            "build_s": round(build_s, 1), "built_on": "device" if args.device_build else "host"},
                 "ns_per_integration": 1e9 / value, "keff": state["keff"], "leakage": leakage,
                 "sweep_ms": state["sweep_ms"] / n_launch,
-                "phases_ms": {"count": state["count_ms"] / n_launch, "fill": state["fill_ms"] / n_launch,
-                              "attenuate": state["att_ms"] / n_launch},
+                "phases_ms": {"count": state["count_ms"] / n_launch, "scan": state["scan_ms"] / n_launch,
+                              "fill": state["fill_ms"] / n_launch, "attenuate": state["att_ms"] / n_launch},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roof, "e2e": e2e,
                 "e2e_full_loop": full_loop, "other_exp_mode": other,
                 "cpu_baseline": cpu}
