@@ -88,6 +88,10 @@ def parse_args():
     ap.add_argument("--no-full-loop", action="store_true", help="skip the e2e_full_loop leg")
     ap.add_argument("--noclamp", type=int, default=1, choices=[0, 1],
                     help="0: keep the table's x > maxVal test in every attenuation launch (A/B timing)")
+    ap.add_argument("--no-numa-bind", action="store_true",
+                    help="N > 1: do not bind each rank to the NUMA node of its GPU")
+    ap.add_argument("--nccl-max-ctas", type=int, default=8,
+                    help="N > 1: NCCL_MAX_CTAS for the boundary exchange (unless the environment already sets it)")
     ap.add_argument("--staged", type=int, default=1, choices=[0, 1],
                     help="1 (default): TMA-staged attenuation kernel; 0: the direct-gather kernel (A/B timing)")
     return ap.parse_args()
@@ -114,6 +118,31 @@ def _workload_input(m, name):
     else:
         inp = m.small_input()
     return inp, WORKLOAD_LABELS[name]
+
+
+def bind_to_gpu_numa_node(torch, local):
+    """One process per GPU on a two-socket host: run this rank's host threads -- and, through first touch, place its
+    pinned host buffers (7 GB up + 7 GB down per step on the default problem) -- on the NUMA node the GPU hangs off,
+    instead of wherever the launcher left the process.  Returns a short description for the JSON line."""
+    try:
+        props = torch.cuda.get_device_properties(local)
+        bus = f"{props.pci_domain_id:04x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return f"gpu {bus}: no NUMA node reported"
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if not allowed:
+            return f"gpu {bus}: node {node} has no CPU this process may use"
+        os.sched_setaffinity(0, allowed)
+        return f"gpu {bus}: bound to NUMA node {node} ({len(allowed)} CPUs)"
+    except (OSError, ValueError, AttributeError) as e:
+        return f"not bound ({type(e).__name__}: {e})"
 
 
 def grid_for(n, spec):
@@ -463,8 +492,12 @@ def run_moc(args):
     if not torch.cuda.is_available() or api.device_count() == 0:
         raise SystemExit("bench.py: no CUDA device -- the MOC path has no CPU fallback")
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa_node(torch, local) if (world > 1 and not args.no_numa_bind) else "not requested"
     dist = None
     if world > 1:
+        # the exchange runs UNDER the interior sweep: NCCL's copy kernels need a few CTAs, not half the machine
+        # (3.2 GB per GPU at 2x2x2 against a 390 ms sweep); the user's own settings win
+        os.environ.setdefault("NCCL_MAX_CTAS", str(args.nccl_max_ctas))
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -622,7 +655,8 @@ def run_moc(args):
                            "l2": f"inputs larger than L2 ({8e-9 * T3 * G:.1f} GB angular flux + "
                                  f"{12e-9 * state['segments'] / n_launch:.1f} GB segment records streamed per "
                                  "step, 126 MB L2); no flush",
-                           "build_s": round(build_s, 1), "built_on": "device" if args.device_build else "host"},
+                           "build_s": round(build_s, 1), "built_on": "device" if args.device_build else "host",
+                           "numa": numa, "nccl_max_ctas": os.environ.get("NCCL_MAX_CTAS") if world > 1 else None},
                 "ns_per_integration": 1e9 / value, "keff": state["keff"], "leakage": leakage,
                 "sweep_ms": state["sweep_ms"] / n_launch,
                 "phases_ms": {"count": state["count_ms"] / n_launch, "scan": state["scan_ms"] / n_launch,
@@ -704,9 +738,19 @@ def measure_e2e(args, m, api, host, dev, torch, dist, world, rank, local, grid):
     d2h = 40 * T3 + 4 * T3 * G + 4 * F * N * G               # Track image, forward flux rows, scalar flux
     e2e = {"value": segs * G / dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
            "steps": steps, "ms_per_step": 1e3 * dt / steps, "host_wall_ms_per_step": 1e3 * wall / steps,
+           "copy_gbs_per_rank_each_way": h2d * steps / dt / 1e9,
            "call": "transport_sweep(Params*, Input*) on host structures (drop-in C-ABI), CUDA events on "
                    "the library's stream around upload + sweep + download; times the sweep only, like the "
                    "metric (utils.c:147-155) and the reference arm -- the whole iteration is e2e_full_loop"}
+    # the same call when the caller promises not to modify its structures between calls (moc_dropin_trust_device):
+    # uploads are skipped, every result is still written back.  NOT the headline e2e (its inputs do not travel).
+    L.moc_dropin_trust_device(1)
+    segs, dt, wall = timed(sweep_only)
+    L.moc_dropin_trust_device(0)
+    e2e["trust_device"] = {"value": segs * G / dt, "ms_per_step": 1e3 * dt / steps, "h2d_bytes_per_step": 0,
+                           "d2h_bytes_per_step": d2h,
+                           "what": "moc_dropin_trust_device(1): the caller only reads its structures between calls; uploads "
+                                   "skipped, downloads kept (informational: the headline e2e is the strict mode above)"}
     full = None
     if not args.no_full_loop:
         keff = [1.0]

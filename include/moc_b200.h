@@ -177,6 +177,12 @@ void moc_dropin_configure(unsigned long long seed, unsigned long long rand_base,
 int moc_set_device(int device);
 /* 1: keep results on the device between the calls above; 0 (default): write back */
 void moc_set_resident(int on);
+/* Half way between the two: 1 = the caller promises not to MODIFY the host structures between drop-in calls
+ * except through these calls (reading them is fine: the reference's main.c only prints).  Uploads are then
+ * skipped -- the device copy is what the library last wrote back -- and every call still writes its results to the
+ * host structures: half the traffic of the default.  0 (default): the host is authoritative, every call uploads
+ * what it reads. */
+void moc_dropin_trust_device(int on);
 /* Resident mode only: tell the library the neighbour table before the loop.  transport_sweep then
  * starts the boundary exchange (comms.c:5-196) as soon as the z-stacks it moves are swept and runs it
  * under the sweep of the interior stacks; the fast_transfer_boundary_fluxes call that follows with the

@@ -94,7 +94,7 @@ _HOST_DTYPE = {HOST_N_SEGMENTS: np.int64, HOST_XS_INDEX: np.int32, ARR_SEG_COUNT
 EXPORTED = [
     "transport_sweep", "renormalize_flux", "update_sources", "compute_keff",
     "fast_transfer_boundary_fluxes", "moc_dropin_configure", "moc_set_device", "moc_handle_of",
-    "moc_set_resident", "moc_dropin_set_grid", "moc_sync_to_host", "moc_release",
+    "moc_set_resident", "moc_dropin_trust_device", "moc_dropin_set_grid", "moc_sync_to_host", "moc_release",
     "moc_create", "moc_create_synthetic", "moc_destroy", "moc_set_option", "moc_get_option", "moc_sweep",
     "moc_renormalize", "moc_update_sources", "moc_compute_keff", "moc_exchange", "moc_sweep_exchange",
     "moc_get_sweep_timing", "moc_get_array", "moc_set_array", "moc_download", "moc_upload",
@@ -177,6 +177,7 @@ def lib():
     L.fast_transfer_boundary_fluxes.restype = None
     L.fast_transfer_boundary_fluxes.argtypes = [Params, Input, CommGrid]
     L.moc_set_resident.argtypes = [C.c_int]
+    L.moc_dropin_trust_device.argtypes = [C.c_int]
     L.moc_set_device.argtypes = [C.c_int]
     L.moc_sync_to_host.argtypes = [C.POINTER(Params)]
     L.moc_dropin_set_grid.argtypes = [C.POINTER(CommGrid)]

@@ -491,7 +491,7 @@ __global__ void __launch_bounds__(128, MOC_ATT_MIN_BLOCKS) attenuate_kernel(cons
 
 
 #ifndef MOC_ABLATE
-#define MOC_ABLATE 0   // experiments only: 1 = no operand copies, 2 = no reductions, 3 = neither (tools/gpu_runs)
+#define MOC_ABLATE 0   // experiments only: 1 = no operand copies, 2 = no reductions, 3 = neither (profiles/r02_K1_findings.md)
 #endif
 
 // ------------------------------------------------------------------ K1 with the gathers staged by the TMA unit

@@ -638,7 +638,7 @@ static int create_common(const Input *I, const Params *P, int device, int source
     if ((rc = dev_alloc(&h->d.per_fine, N * F))) return fail(rc);
     if ((rc = dev_alloc(&h->d.scalars, 8))) return fail(rc);
     if ((rc = dev_alloc(&h->d.leakage, 1))) return fail(rc);
-    if (cudaHostAlloc((void **)&h->pair_base_pinned, sizeof(unsigned long long) * 2 * (pairs + 1), cudaHostAllocDefault) != cudaSuccess) {
+    if (cudaHostAlloc((void **)&h->pair_base_pinned, sizeof(unsigned long long) * (2 * (pairs + 1) + 1), cudaHostAllocDefault) != cudaSuccess) {
         moc_set_error("cudaHostAlloc(pair_base) failed");
         return fail(MOC_ENOMEM);
     }

@@ -13,6 +13,7 @@ struct Mirror {
 static std::mutex g_mirror_mutex;
 static std::unordered_map<const void *, Mirror> g_mirrors;   // keyed by Params.tracks
 static int g_resident = 0;
+static int g_trust_device = 0;
 static unsigned long long g_dropin_seed = 1, g_dropin_rand_base = 0;
 static bool g_dropin_configured = false;
 static int g_dropin_exp_mode = 0, g_dropin_source_stride = 48;
@@ -28,6 +29,13 @@ extern "C" void moc_dropin_set_grid(const CommGrid *grid)
 }
 
 extern "C" void moc_set_resident(int on) { g_resident = on ? 1 : 0; }
+
+// Between resident (nothing moves) and the default (every call uploads what it reads and downloads what it writes):
+// the caller promises not to modify the host structures between drop-in calls except through these calls.  The device
+// copy then always equals the host copy, uploads are skipped (a mirror still takes everything when it is built), and
+// every call still writes its results back -- a caller that only READS its structures between calls (prints, dumps,
+// convergence checks: the reference's own main.c) sees exactly what the default gives it, for half the traffic.
+extern "C" void moc_dropin_trust_device(int on) { g_trust_device = on ? 1 : 0; }
 
 extern "C" int moc_set_device(int device)
 {
@@ -203,7 +211,7 @@ static Mirror &mirror_for(const Params *P, const Input *I, HostLayout &L, int re
     // resident mode, find every array defined
     int parts = reads;
     if (created) parts = PART_TRACKS | PART_PSI_F | PART_PSI_B | PART_SOURCE | PART_FLUX | PART_SIGT | PART_LEAKAGE;
-    else if (g_resident) parts = 0;
+    else if (g_resident || g_trust_device) parts = 0;
     if (parts && move_parts(m.h, L, P, parts, true, (parts & PART_PSI_HEAD) && grid ? exchange_head_floats(m.h, grid) : 0))
         die(where);
     return m;
@@ -242,7 +250,8 @@ static int renormalize_streamed(Mirror &m, const HostLayout &L, const Params *P)
         cudaEvent_t e_up, e_done;
         if ((rc = event_at(h, ev_next++, &e_up))) return rc;
         if ((rc = event_at(h, ev_next++, &e_done))) return rc;
-        CUDA_TRY(cudaMemcpyAsync(h->d.psi + first, L.psi + first, sizeof(float) * (size_t)count, cudaMemcpyHostToDevice, h->up_stream));
+        if (!g_trust_device)
+            CUDA_TRY(cudaMemcpyAsync(h->d.psi + first, L.psi + first, sizeof(float) * (size_t)count, cudaMemcpyHostToDevice, h->up_stream));
         CUDA_TRY(cudaEventRecord(e_up, h->up_stream));
         CUDA_TRY(cudaStreamWaitEvent(h->stream, e_up, 0));
         scale_psi_range(h, first, count, h->stream);
@@ -270,7 +279,7 @@ extern "C" void transport_sweep(Params *params, Input *I)
         for (int q = 0; q < 12; q++) peers = peers || nb[q] >= 0;
         if (!peers || m.h->nccl_comm) ahead = &g_dropin_grid;   // neighbours need moc_comm_init first
     }
-    if (sweep_core(m.h, &segs, g_resident ? nullptr : &L, ahead)) die("transport_sweep");
+    if (sweep_core(m.h, &segs, g_resident ? nullptr : &L, ahead, !g_trust_device)) die("transport_sweep");
     m.exchanged = ahead != nullptr;
     I->segments_processed = segs;
     if (g_resident) m.dirty_sweep = true;

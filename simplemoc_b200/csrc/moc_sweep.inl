@@ -341,8 +341,10 @@ static int event_at(moc_handle *h, size_t idx, cudaEvent_t *out)
 // overlap_grid != nullptr (resident problem only): the boundary exchange of comms.c is started on a
 // second stream as soon as the z-stacks whose angular flux it moves -- the first tracks of the
 // slab, comms.c:100-183 -- have been swept, and runs under the sweep of the interior stacks.
+// io_upload = false (moc_dropin_trust_device): the device copy is what the library last wrote to / read from the host
+// structures and the caller promises it has not changed them since: only the downloads happen.
 static int sweep_core(moc_handle *h, long *segments_processed, const HostLayout *io,
-                      const CommGrid *overlap_grid = nullptr)
+                      const CommGrid *overlap_grid = nullptr, bool io_upload = true)
 {
     CUDA_TRY(cudaSetDevice(h->device));
     const long long pairs = h->T2 * h->P;
@@ -390,25 +392,44 @@ static int sweep_core(moc_handle *h, long *segments_processed, const HostLayout 
         cudaEvent_t e_img;
         if ((rc = event_at(h, ev_next++, &e_img))) return rc;
         CUDA_TRY(cudaStreamWaitEvent(h->up_stream, e_start, 0));
-        CUDA_TRY(cudaMemcpyAsync(h->d.track_image, io->tracks, sizeof(TrackImage) * (size_t)h->T3,
-                                 cudaMemcpyHostToDevice, h->up_stream));
-        CUDA_TRY(cudaMemcpy2DAsync(h->d.src, sizeof(float) * h->Gp, io->src, sizeof(float) * G, sizeof(float) * G,
-                                   (size_t)(2 * h->F + 1) * (size_t)h->N, cudaMemcpyHostToDevice, h->up_stream));
+        if (io_upload) {
+            CUDA_TRY(cudaMemcpyAsync(h->d.track_image, io->tracks, sizeof(TrackImage) * (size_t)h->T3,
+                                     cudaMemcpyHostToDevice, h->up_stream));
+            CUDA_TRY(cudaMemcpy2DAsync(h->d.src, sizeof(float) * h->Gp, io->src, sizeof(float) * G, sizeof(float) * G,
+                                       (size_t)(2 * h->F + 1) * (size_t)h->N, cudaMemcpyHostToDevice, h->up_stream));
+            h->sigT_known = false;
+        }
         CUDA_TRY(cudaEventRecord(e_img, h->up_stream));
         for (size_t c = 0; c < n_chunks; c++) {
             const size_t t0 = (size_t)chunk_first[c] * h->Z, t1 = (size_t)chunk_first[c + 1] * h->Z;
             // forward rows only: row pitch 2*G floats on both sides
-            CUDA_TRY(cudaMemcpy2DAsync(h->d.psi + 2 * t0 * G, sizeof(float) * 2 * G, io->psi + 2 * t0 * G,
-                                       sizeof(float) * 2 * G, sizeof(float) * G, t1 - t0, cudaMemcpyHostToDevice,
-                                       h->up_stream));
+            if (io_upload)
+                CUDA_TRY(cudaMemcpy2DAsync(h->d.psi + 2 * t0 * G, sizeof(float) * 2 * G, io->psi + 2 * t0 * G,
+                                           sizeof(float) * 2 * G, sizeof(float) * G, t1 - t0, cudaMemcpyHostToDevice,
+                                           h->up_stream));
             if ((rc = event_at(h, ev_next++, &ev_up[c]))) return rc;
             CUDA_TRY(cudaEventRecord(ev_up[c], h->up_stream));
         }
         CUDA_TRY(cudaStreamWaitEvent(h->stream, e_img, 0));
-        const int threads = 256;
-        unpack_tracks_kernel<<<(unsigned)((h->T3 + threads - 1) / threads), threads, 0, h->stream>>>(
-            h->d.track_image, h->T3, h->d.p_weight, h->d.z_height);
+        if (io_upload) {
+            const int threads = 256;
+            unpack_tracks_kernel<<<(unsigned)((h->T3 + threads - 1) / threads), threads, 0, h->stream>>>(
+                h->d.track_image, h->T3, h->d.p_weight, h->d.z_height);
+            h->launch_count++;
+        }
+    }
+
+    // the largest sigT of the slab, if the slab changed since it was last looked for (see ds_noclamp below)
+    unsigned int *const sigt_host = reinterpret_cast<unsigned int *>(h->pair_base_pinned + 2 * (pairs + 1));
+    const bool sigt_pending = h->allow_noclamp && !h->sigT_known;
+    if (sigt_pending) {
+        unsigned int *out = reinterpret_cast<unsigned int *>(h->d.digest + 5);
+        sigt_host[0] = 0;
+        sigt_host[1] = 1;
+        CUDA_TRY(cudaMemsetAsync(out, 0, 2 * sizeof(unsigned int), h->stream));
+        sigt_range_kernel<<<148 * 4, 256, 0, h->stream>>>(h->d.src + (size_t)2 * h->N * h->F * h->Gp, h->N, h->G, h->Gp, out);
         h->launch_count++;
+        CUDA_TRY(cudaMemcpyAsync(sigt_host, out, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, h->stream));
     }
 
     // ---- pass 1: segment counts per ray and per (2D track, polar angle) stack
@@ -442,6 +463,11 @@ static int sweep_core(moc_handle *h, long *segments_processed, const HostLayout 
     // and the batches are sized by; the segment total is the last entry of the serial scan
     const unsigned long long *base = h->pair_base_pinned + pairs + 1;
     const unsigned long long total = h->pair_base_pinned[pairs];
+    if (sigt_pending) {
+        memcpy(&h->sigT_max, &sigt_host[0], sizeof(float));
+        h->sigT_clean = sigt_host[1] == 0;
+        h->sigT_known = true;
+    }
 
     // ---- batches of whole stacks whose records fit the staging buffers (never across a chunk)
     unsigned long long largest_pair = 0, largest_chunk = 0;
@@ -531,24 +557,11 @@ static int sweep_core(moc_handle *h, long *segments_processed, const HostLayout 
 
     // Which segments may skip the reference's x > maxVal test of the table (solver.c:1444-1445)?  Those whose optical
     // length cannot get there with ANY cross section of the slab: ds <= 0.99 maxVal / (largest sigT).  The largest sigT
-    // is found once per upload of the slab (resident problems: once); a slab with a negative or non-finite value, or one
-    // the host streams in with every call, keeps the test everywhere.
+    // was looked for when the slab last changed (sigt_range_kernel, queued in front of the ray trace and read with the
+    // scan's results); a slab with a negative or non-finite value keeps the test everywhere.
     a.ds_noclamp = 0.f;
-    if (!io && h->allow_noclamp) {
-        if (!h->sigT_known) {
-            unsigned int *out = reinterpret_cast<unsigned int *>(h->d.digest + 5), host_out[2] = {0, 1};
-            CUDA_TRY(cudaMemsetAsync(out, 0, 2 * sizeof(unsigned int), h->stream));
-            sigt_range_kernel<<<148 * 4, 256, 0, h->stream>>>(a.sigT, h->N, h->G, h->Gp, out);
-            h->launch_count++;
-            CUDA_TRY(cudaMemcpyAsync(host_out, out, sizeof host_out, cudaMemcpyDeviceToHost, h->stream));
-            CUDA_TRY(cudaStreamSynchronize(h->stream));
-            memcpy(&h->sigT_max, &host_out[0], sizeof(float));
-            h->sigT_clean = host_out[1] == 0;
-            h->sigT_known = true;
-        }
-        if (h->sigT_clean && h->table_max > 0.f)
-            a.ds_noclamp = h->sigT_max > 0.f ? (float)(0.99 * (double)h->table_max / (double)h->sigT_max) : 3.0e38f;
-    }
+    if (h->allow_noclamp && h->sigT_known && h->sigT_clean && h->table_max > 0.f)
+        a.ds_noclamp = h->sigT_max > 0.f ? (float)(0.99 * (double)h->table_max / (double)h->sigT_max) : 3.0e38f;
     h->noclamp_now = a.ds_noclamp > 0.f;
     h->staged_now = staged_applies(h);
     if (h->staged_now && !h->d.coef4 && (rc = dev_alloc(&h->d.coef4, (size_t)h->N * (h->F - 2) * 4 * (size_t)h->G))) return rc;

@@ -37,7 +37,7 @@
  */
 #pragma once
 
-// Both on by default; 0 restores the per-lane forms (kept for A/B timing: tools/gpu_runs).
+// Both on by default; 0 restores the per-lane forms (kept for A/B timing).
 #ifndef MOC_WALK_COMPACT_CROSSING
 #define MOC_WALK_COMPACT_CROSSING 1
 #endif

@@ -383,6 +383,29 @@ def test_dropin_names_on_the_reference_own_structures(built):
             a, b = getattr(mine, name), getattr(theirs, name)
             assert rel_l2(a, b) <= TOL, (name, chunks, batch)
     assert L.moc_set_option(mirror, api.OPT_BATCH_SEGMENTS, 0) == 0
+    # moc_dropin_trust_device: the caller only reads its structures between calls -> uploads are skipped, results still
+    # land in the host structures after every call (two iterations of the reference's loop, main.c:57-92)
+    L.moc_dropin_trust_device(1)
+    for it in range(2):
+        L.transport_sweep(C.byref(params), C.byref(inp))
+        assert inp.segments_processed == theirs.sweep()
+        assert np.array_equal(mine.z_height, theirs.z_height)
+        L.renormalize_flux(params, inp, grid); theirs.renormalize()
+        res = L.update_sources(params, inp, 1.0); res_cpu = theirs.update_sources(1.0)
+        k, k_cpu = L.compute_keff(params, inp, grid), theirs.compute_keff()
+        if it == 0:
+            assert abs(k - k_cpu) <= TOL * abs(k_cpu)
+            for name in ("fine_flux", "psi", "fine_source"):
+                assert rel_l2(getattr(mine, name), getattr(theirs, name)) <= TOL, name
+    L.moc_dropin_trust_device(0)
+    # ... and back in the default mode the host is authoritative again: a change made on the host is seen
+    mine.fine_flux[...] = theirs.fine_flux
+    mine.psi[...] = theirs.psi
+    mine.fine_source[...] = theirs.fine_source
+    L.transport_sweep(C.byref(params), C.byref(inp))
+    assert inp.segments_processed == theirs.sweep()
+    for name in ("fine_flux", "psi"):
+        assert rel_l2(getattr(mine, name), getattr(theirs, name)) <= TOL, name
     # resident mode: nothing comes back until moc_sync_to_host
     L.moc_set_resident(1)
     before = mine.fine_flux.copy()
