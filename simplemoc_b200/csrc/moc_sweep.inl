@@ -410,6 +410,9 @@ static int sweep_core(moc_handle *h, long *segments_processed, const HostLayout 
             if ((rc = event_at(h, ev_next++, &ev_up[c]))) return rc;
             CUDA_TRY(cudaEventRecord(ev_up[c], h->up_stream));
         }
+        // (Tried: downloads held back until the last upload of the call, because eight ranks of one box move 184 GB/s in
+        // one direction against 2 x 64 GB/s in both at once -- profiles/r02_host_copy_probe_n8.json.  The downloads are the
+        // slow direction, 83 GB/s for all eight ranks alone: 965 instead of 915 ms per call at 8 ranks.  Not kept.)
         CUDA_TRY(cudaStreamWaitEvent(h->stream, e_img, 0));
         if (io_upload) {
             const int threads = 256;
