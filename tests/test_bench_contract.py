@@ -9,8 +9,10 @@ import re
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LINES = sorted(glob.glob(os.path.join(ROOT, "profiles", "r01_bench_default_v[45].json")) +
-               glob.glob(os.path.join(ROOT, "profiles", "r01_bench_n2_2x1x1_v5.json")))
+LINES = sorted(glob.glob(os.path.join(ROOT, "profiles", "r02_bench_default.json")) +
+               glob.glob(os.path.join(ROOT, "profiles", "r02_bench_default_sfu.json")) +
+               glob.glob(os.path.join(ROOT, "profiles", "r02_bench_config5.json")) +
+               glob.glob(os.path.join(ROOT, "profiles", "r02_bench_n[28].json")))
 BASE = ["metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
         "vs_baseline", "dtype", "data", "config", "gpu_launches", "clocks", "roofline"]
 
@@ -35,14 +37,29 @@ def test_committed_bench_lines_follow_the_contract(path):
     r = d["roofline"]
     for k in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
         assert k in r, k
-    assert r["bound"] in ("hbm", "tensor") and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    # "fp32": the round-1 verdict asked for the binding pipe (FMA / issue) as the headline fraction of the L2-resident
+    # configurations, with HBM beside it; config 5 (slab larger than the L2) is "hbm" from an ncu capture
+    assert r["bound"] in ("hbm", "tensor", "fp32") and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    assert r["unit"] == ("GB/s" if r["bound"] == "hbm" else "TFLOP/s")
+    assert "algorithmic_bytes" in r and "hbm" in r and {"achieved_gbs", "peak_gbs", "frac"} <= set(r["hbm"])
+    if r["bound"] == "fp32":
+        assert 0.3 < r["frac"] < 1.0 and 0.5 < r["issue"]["frac_of_issue_slots"] <= 1.0
+        assert r["traffic"] is None or r["hbm"]["traffic_over_algorithmic"] > 1.0
+    else:
+        assert 0.5 < r["frac"] <= 1.05 and r["traffic"] and "ncu" in r["achieved_from"]
+    if d["n_gpus"] > 1:
+        x = d["exchange_parity"]
+        assert x["result"] == "bit-exact" and x["ranks"] == d["n_gpus"]
     c = d["clocks"]
     assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(c)
     assert not {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"} & set(c["reasons"])
-    if d["n_gpus"] == 1 and "e2e" in d:
+    if d["n_gpus"] == 1 and d.get("e2e"):
         e = d["e2e"]
         assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(e)
         assert e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and e["value"] < d["value"]
         b = d["cpu_baseline"]
-        assert {"value", "unit", "cores", "kind", "sample"} <= set(b) and b["kind"] in ("reference", "port")
+        if b:
+            assert {"value", "unit", "cores", "kind", "sample"} <= set(b) and b["kind"] in ("reference", "port")
+        if d.get("e2e_full_loop"):
+            assert d["e2e_full_loop"]["ms_per_step"] > e["ms_per_step"]
     assert isinstance(baseline, dict)

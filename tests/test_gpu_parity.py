@@ -428,3 +428,37 @@ def test_randomised_configurations(built):
                        capture_output=True, text=True, timeout=900)
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-2000:]
     assert "25 cases, 0 mismatches" in p.stdout
+
+
+def test_sizes_outside_the_kernels_reach_are_refused_at_create(built):
+    """ADVICE (round 1): a group count no lane mapping covers and an exponential table that does not fit the shared
+    memory of an SM used to pass moc_create and fail inside the first sweep, after both ray-trace passes."""
+    vals = list(CASES["tiny"])
+    vals[9] = 513                                               # n_egroups
+    host = m.HostProblem(m.derive(m.input_from_values(vals)), seed=1)
+    with pytest.raises(m.MocError, match="n_egroups=513"):
+        m.DeviceProblem(host, device=0)
+    host.close()
+    vals = list(CASES["tiny"])
+    vals[15] = 1e-7                                             # precision -> 111 803 table cells
+    host = m.HostProblem(m.derive(m.input_from_values(vals)), seed=1)
+    with pytest.raises(m.MocError, match="exponential table"):
+        m.DeviceProblem(host, device=0)
+    host.close()
+
+
+@pytest.mark.parametrize("case", ["tiny", "mini104"])
+def test_fine_exponential_table_above_48_kb(built, case):
+    """Input.precision = 2e-5 -> 7 905 table cells = 63 KB of shared memory: needs the opt-in attribute (both attenuation
+    kernels); same parity bar as the default table."""
+    vals = list(CASES[case])
+    vals[15] = 2e-5
+    host = m.HostProblem(m.derive(m.input_from_values(vals)), seed=3)
+    dev = m.DeviceProblem(host, device=0)
+    dev.set_option(api.OPT_DIGEST, 1)
+    oracle = OracleCase(vals, seed=3)
+    assert oracle.table[3] > 6143
+    assert dev.sweep() == oracle.sweep()
+    assert np.array_equal(dev.get(api.ARR_QSR_DIGEST), oracle.digest)
+    check_state(dev, oracle, f"{case} fine table", noise_cap=NOISE_CAP)
+    dev.close(); host.close(); oracle.close()
