@@ -239,7 +239,8 @@ enum {
     MOC_ARR_Z_HEIGHT = 5,    /* float [ntracks]                                  */
     MOC_ARR_P_WEIGHT = 6,    /* float [ntracks]                                  */
     MOC_ARR_SEG_COUNT = 7,   /* uint32 [ntracks]: 3D segments of each track in the last sweep */
-    MOC_ARR_QSR_DIGEST = 8   /* uint64 [4]: n, sum(row), sum(row*idx mix), xor-hash: see DESIGN.md */
+    MOC_ARR_QSR_DIGEST = 8,  /* uint64 [4]: n, sum(row), sum(row*idx mix), xor-hash: see DESIGN.md */
+    MOC_ARR_QSR_DIGEST_BACK = 9 /* uint64 [4]: the same over the backward pass of moc_two_way_sweep, keyed track*4096+segment */
 };
 
 /* timing of the last moc_sweep, CUDA events, milliseconds */
@@ -268,6 +269,12 @@ int moc_set_option(moc_handle *h, int option, long value);
 long moc_get_option(moc_handle *h, int option);
 
 int moc_sweep(moc_handle *h, long *segments_processed);        /* transport_sweep   */
+/* two_way_transport_sweep (src/solver.c:556-891; compiled into the reference, called from nowhere): every ray is
+ * walked forward into the forward angular flux, then retraced last segment first into the backward one.
+ * *segments_processed counts both passes, and only for axial_exp == 2 (solver.c:752, 826).  Where a step length
+ * comes out negative (solver.c:686) the reference's exponential table is read in front of its first cell; this
+ * library answers from cell 0, like oracle/moc_oracle.c. */
+int moc_two_way_sweep(moc_handle *h, long *segments_processed);
 int moc_renormalize(moc_handle *h);                            /* renormalize_flux  */
 int moc_update_sources(moc_handle *h, float keff, float *res); /* update_sources    */
 int moc_compute_keff(moc_handle *h, float *keff);              /* compute_keff      */

@@ -86,6 +86,7 @@ OPT_STAGED = 104            # 1 (default): TMA-staged attenuation kernel where i
 EXP_TABLE_REF, EXP_SFU = 0, 1
 ARR_FINE_SOURCE, ARR_FINE_FLUX, ARR_SIGT, ARR_PSI, ARR_Z_HEIGHT, ARR_P_WEIGHT, ARR_SEG_COUNT, ARR_QSR_DIGEST = \
     1, 2, 3, 4, 5, 6, 7, 8
+ARR_QSR_DIGEST_BACK = 9     # the backward pass of two_way_sweep
 (HOST_AZ_WEIGHT, HOST_N_SEGMENTS, HOST_SEG_LENGTHS, HOST_XS, HOST_SCATTER, HOST_XS_INDEX, HOST_VOL,
  HOST_POLAR, HOST_TABLE) = range(20, 29)
 _HOST_DTYPE = {HOST_N_SEGMENTS: np.int64, HOST_XS_INDEX: np.int32, ARR_SEG_COUNT: np.uint32}
@@ -95,7 +96,7 @@ EXPORTED = [
     "transport_sweep", "renormalize_flux", "update_sources", "compute_keff",
     "fast_transfer_boundary_fluxes", "moc_dropin_configure", "moc_set_device", "moc_handle_of",
     "moc_set_resident", "moc_dropin_trust_device", "moc_dropin_set_grid", "moc_sync_to_host", "moc_release",
-    "moc_create", "moc_create_synthetic", "moc_destroy", "moc_set_option", "moc_get_option", "moc_sweep",
+    "moc_create", "moc_create_synthetic", "moc_destroy", "moc_set_option", "moc_get_option", "moc_sweep", "moc_two_way_sweep",
     "moc_renormalize", "moc_update_sources", "moc_compute_keff", "moc_exchange", "moc_sweep_exchange",
     "moc_get_sweep_timing", "moc_get_array", "moc_set_array", "moc_download", "moc_upload",
     "moc_get_leakage", "moc_synchronize", "moc_get_stream", "moc_get_launch_count", "moc_probe_l2_gather", "moc_comm_get_unique_id", "moc_comm_init",
@@ -142,6 +143,7 @@ def lib():
     L.moc_get_option.restype = C.c_long
     L.moc_get_option.argtypes = [vp, C.c_int]
     L.moc_sweep.argtypes = [vp, lp]
+    L.moc_two_way_sweep.argtypes = [vp, lp]
     L.moc_renormalize.argtypes = [vp]
     L.moc_update_sources.argtypes = [vp, C.c_float, C.POINTER(C.c_float)]
     L.moc_compute_keff.argtypes = [vp, C.POINTER(C.c_float)]
@@ -341,6 +343,12 @@ class DeviceProblem:
         _check(lib().moc_sweep(self.h, C.byref(n)), "moc_sweep")
         return n.value
 
+    def two_way_sweep(self):
+        """two_way_transport_sweep (solver.c:556-891): forward walk + backward retrace of every ray"""
+        n = C.c_long(0)
+        _check(lib().moc_two_way_sweep(self.h, C.byref(n)), "moc_two_way_sweep")
+        return n.value
+
     def renormalize(self):
         _check(lib().moc_renormalize(self.h), "moc_renormalize")
 
@@ -400,7 +408,8 @@ class DeviceProblem:
             ARR_FINE_SOURCE: ((N, F, G), np.float32), ARR_FINE_FLUX: ((N, F, G), np.float32),
             ARR_SIGT: ((N, G), np.float32), ARR_PSI: ((T3, 2, G), np.float32),
             ARR_Z_HEIGHT: ((T3,), np.float32), ARR_P_WEIGHT: ((T3,), np.float32),
-            ARR_SEG_COUNT: ((T3,), np.uint32), ARR_QSR_DIGEST: ((4,), np.uint64)}[which]
+            ARR_SEG_COUNT: ((T3,), np.uint32), ARR_QSR_DIGEST: ((4,), np.uint64),
+            ARR_QSR_DIGEST_BACK: ((4,), np.uint64)}[which]
 
     def get(self, which):
         shape, dt = self._shape(which)

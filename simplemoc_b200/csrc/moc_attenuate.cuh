@@ -121,6 +121,8 @@ struct SegmentScalars {
 //          is the reference's), IEEE division.
 //  MODE 1: the same with the verified fast division.
 //  MODE 2: SFU: MUFU.EX2.
+//  MODE 6: MODE 0 for the two-way sweep (moc_two_way.cuh), whose negative lengths select cells in front of the table:
+//          answered from cell 0, as the oracle does where the reference reads its heap.
 //  MODE 3 / 4: MODE 1 / 2 without the reference's x > maxVal -> 1 rule (solver.c:1444-1445): for segments so short
 //  that no sigT of the slab can carry the optical length past maxVal (ds <= AttenuateParams::ds_noclamp, decided per
 //  segment and warp) the rule cannot fire and two instructions per group go.  (Not per sweep: in the last 2D segment
@@ -136,7 +138,7 @@ __device__ __forceinline__ void one_minus_exp2(float2 x, const TableConsts &tc, 
         E = sub2(bc(1.0f), D);
     } else {
         float2 t;
-        if (MODE == 0) {
+        if (MODE == 0 || MODE == 6) {
             t.x = __fadd_rn(__fdiv_rn(x.x, tc.dx), tc.half_dx);
             t.y = __fadd_rn(__fdiv_rn(x.y, tc.dx), tc.half_dx);
         } else {
@@ -146,6 +148,10 @@ __device__ __forceinline__ void one_minus_exp2(float2 x, const TableConsts &tc, 
             t = add2(q, bc(tc.half_dx));
         }
         int c0 = __float2int_rz(t.x), c1 = __float2int_rz(t.y);
+        if (MODE == 6) {
+            c0 = max(c0, 0);
+            c1 = max(c1, 0);
+        }
         if (MODE != 3) {
             c0 = x.x > tc.x_max ? tc.n : c0;
             c1 = x.y > tc.x_max ? tc.n : c1;
@@ -170,7 +176,7 @@ __device__ __forceinline__ void one_minus_exp2(float x, const TableConsts &tc, f
         E = __fadd_rn(1.0f, -D);
     } else {
         float t;
-        if (MODE == 0) {
+        if (MODE == 0 || MODE == 6) {
             t = __fadd_rn(__fdiv_rn(x, tc.dx), tc.half_dx);
         } else {
             float q = __fmul_rn(x, tc.rdx);
@@ -179,6 +185,7 @@ __device__ __forceinline__ void one_minus_exp2(float x, const TableConsts &tc, f
             t = __fadd_rn(q, tc.half_dx);
         }
         int c = __float2int_rz(t);
+        if (MODE == 6) c = max(c, 0);
         if (MODE != 3) c = x > tc.x_max ? tc.n : c;
         const float2 e = *reinterpret_cast<const float2 *>(tc.tab + 2 * c);
         E = __fmaf_rn(e.x, x, e.y);

@@ -632,7 +632,8 @@ static int create_common(const Input *I, const Params *P, int device, int source
     if ((rc = dev_alloc(&h->d.pair_base, pairs + 1))) return fail(rc);
     if ((rc = dev_alloc(&h->d.rec_base, pairs + 1))) return fail(rc);
     if ((rc = dev_alloc(&h->d.pair_max, pairs))) return fail(rc);
-    if ((rc = dev_alloc(&h->d.digest, 8))) return fail(rc);   // [4]: ray-trace flags, [5]: sigT range (sweep_core)
+    if ((rc = dev_alloc(&h->d.digest, 12))) return fail(rc);   // [4]: ray-trace flags, [5]: sigT range (sweep_core),
+                                                                // [8..11]: backward digest of the two-way sweep
     if ((rc = dev_alloc(&h->d.per_region_a, N))) return fail(rc);
     if ((rc = dev_alloc(&h->d.per_region_b, N))) return fail(rc);
     if ((rc = dev_alloc(&h->d.per_fine, N * F))) return fail(rc);
@@ -643,7 +644,7 @@ static int create_common(const Input *I, const Params *P, int device, int source
         return fail(MOC_ENOMEM);
     }
     cudaMemsetAsync(h->d.seg_count, 0, sizeof(uint32_t) * T3, h->stream);
-    cudaMemsetAsync(h->d.digest, 0, sizeof(unsigned long long) * 8, h->stream);
+    cudaMemsetAsync(h->d.digest, 0, sizeof(unsigned long long) * 12, h->stream);
     cudaMemsetAsync(h->d.scalars, 0, sizeof(float) * 8, h->stream);
     h->leakage_host = P->leakage ? *P->leakage : 0.f;
     cudaMemcpyAsync(h->d.leakage, &h->leakage_host, sizeof(float), cudaMemcpyHostToDevice, h->stream);
@@ -792,6 +793,7 @@ extern "C" long moc_get_option(moc_handle *h, int option)
 
 // The rest of this translation unit, in the order it is compiled:
 #include "moc_sweep.inl"    // the transport sweep
+#include "moc_two_way.inl"  // two_way_transport_sweep
 #include "moc_phases.inl"   // renormalise, update_sources, k-eff, array access
 #include "moc_comm.inl"     // boundary exchange over NCCL
 #include "moc_dropin.inl"   // the reference's names on host structures

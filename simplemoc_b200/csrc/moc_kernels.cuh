@@ -427,6 +427,7 @@ __global__ void pair_scan_kernel(const unsigned long long *count, const unsigned
 
 // ------------------------------------------------------------------ K1: attenuation
 #include "moc_attenuate.cuh"
+#include "moc_two_way.cuh"   // two_way_transport_sweep (coverage path)
 
 // ------------------------------------------------------------------ exact pairwise sums
 

@@ -132,6 +132,7 @@ static int array_span(moc_handle *h, int which, void **ptr, size_t *bytes, size_
     case MOC_ARR_P_WEIGHT: *ptr = h->d.p_weight; *bytes = sizeof(float) * T3; return MOC_OK;
     case MOC_ARR_SEG_COUNT: *ptr = h->d.seg_count; *bytes = sizeof(uint32_t) * T3; return MOC_OK;
     case MOC_ARR_QSR_DIGEST: *ptr = h->d.digest; *bytes = sizeof(unsigned long long) * 4; return MOC_OK;
+    case MOC_ARR_QSR_DIGEST_BACK: *ptr = h->d.digest + 8; *bytes = sizeof(unsigned long long) * 4; return MOC_OK;
     }
     moc_set_error("unknown array id %d", which);
     return MOC_EINVAL;
@@ -163,7 +164,7 @@ extern "C" int moc_set_array(moc_handle *h, int which, const void *src, size_t b
     size_t n, row0, rows;
     int rc = array_span(h, which, &p, &n, &row0, &rows);
     if (rc) return rc;
-    if (bytes != n || which == MOC_ARR_SEG_COUNT || which == MOC_ARR_QSR_DIGEST) {
+    if (bytes != n || which == MOC_ARR_SEG_COUNT || which == MOC_ARR_QSR_DIGEST || which == MOC_ARR_QSR_DIGEST_BACK) {
         moc_set_error("moc_set_array(%d): read-only array or size mismatch (%zu vs %zu)", which, bytes, n);
         return MOC_EINVAL;
     }

@@ -315,6 +315,42 @@ static int ensure_record_capacity(moc_handle *h, long long records)
     return MOC_OK;
 }
 
+// everything of AttenuateParams that does not depend on the batch
+static AttenuateParams attenuate_params(const moc_handle *h, const WalkParams &w)
+{
+    AttenuateParams a;
+    memset(&a, 0, sizeof a);
+    a.rec_ds = h->d.rec_ds;
+    a.rec_zin = h->d.rec_zin;
+    a.rec_code = h->d.rec_code;
+    a.rec_base = h->d.rec_base;
+    a.Zs = w.Zs;
+    a.seg_count = h->d.seg_count;
+    a.p_weight = h->d.p_weight;
+    a.az_weight = h->d.az_weight;
+    a.mu = h->d.mu;
+    a.psi = h->d.psi;
+    a.fine_source = h->d.src;
+    a.coef = h->fit_per_segment ? nullptr : h->d.coef;
+    a.coef_stencils = h->F - 2;
+    a.inv_2dz = 1.0f / (2.f * w.dz_fine);
+    a.inv_2dz2 = 1.0f / (2.f * w.dz_fine * w.dz_fine);
+    a.fine_flux = h->d.src + (size_t)h->N * h->F * h->Gp;
+    a.sigT = h->d.src + (size_t)2 * h->N * h->F * h->Gp;
+    a.pitch = h->Gp;
+    a.table = h->d.table;
+    a.table_dx = h->table_dx;
+    a.table_rdx = 1.0f / h->table_dx;
+    a.table_max = h->table_max;
+    a.table_half_dx = 0.5f * h->table_dx;
+    a.table_n = h->table_n;
+    a.P = h->P;
+    a.Z = h->Z;
+    a.G = h->G;
+    a.fai = h->F;
+    return a;
+}
+
 static int exchange_on_stream(moc_handle *h, const CommGrid *grid, cudaStream_t st);   // comms section
 static int ensure_exchange_stage(moc_handle *h, long n_recv, long long chunk);
 static long exchange_receives(moc_handle *h, const CommGrid *grid, long long *chunk);
@@ -527,36 +563,7 @@ static int sweep_core(moc_handle *h, long *segments_processed, const HostLayout 
     if ((rc = ensure_record_capacity(h, std::max<long long>(need, 1)))) return rc;
     w = walk_params(h);   // record pointers may have changed
 
-    AttenuateParams a;
-    memset(&a, 0, sizeof a);
-    a.rec_ds = h->d.rec_ds;
-    a.rec_zin = h->d.rec_zin;
-    a.rec_code = h->d.rec_code;
-    a.rec_base = h->d.rec_base;
-    a.Zs = w.Zs;
-    a.seg_count = h->d.seg_count;
-    a.p_weight = h->d.p_weight;
-    a.az_weight = h->d.az_weight;
-    a.mu = h->d.mu;
-    a.psi = h->d.psi;
-    a.fine_source = h->d.src;
-    a.coef = h->fit_per_segment ? nullptr : h->d.coef;
-    a.coef_stencils = h->F - 2;
-    a.inv_2dz = 1.0f / (2.f * w.dz_fine);
-    a.inv_2dz2 = 1.0f / (2.f * w.dz_fine * w.dz_fine);
-    a.fine_flux = h->d.src + (size_t)h->N * h->F * h->Gp;
-    a.sigT = h->d.src + (size_t)2 * h->N * h->F * h->Gp;
-    a.pitch = h->Gp;
-    a.table = h->d.table;
-    a.table_dx = h->table_dx;
-    a.table_rdx = 1.0f / h->table_dx;
-    a.table_max = h->table_max;
-    a.table_half_dx = 0.5f * h->table_dx;
-    a.table_n = h->table_n;
-    a.P = h->P;
-    a.Z = h->Z;
-    a.G = h->G;
-    a.fai = h->F;
+    AttenuateParams a = attenuate_params(h, w);
 
     // Which segments may skip the reference's x > maxVal test of the table (solver.c:1444-1445)?  Those whose optical
     // length cannot get there with ANY cross section of the slab: ds <= 0.99 maxVal / (largest sigT).  The largest sigT
