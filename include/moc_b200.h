@@ -151,6 +151,10 @@ typedef struct {
 /* src/solver.c:283-552.  Mutates tracks[][][].z_height, f_psi, sources[].fine_flux;
  * writes I->segments_processed. */
 void transport_sweep(Params *params, Input *I);
+/* src/solver.c:556-891 (defined in the reference, declared in none of its headers, called from nowhere).
+ * Mutates f_psi AND b_psi, sources[].fine_flux; leaves every z_height at its start value; writes
+ * I->segments_processed (both passes; 0 for the flat source). */
+void two_way_transport_sweep(Params *params, Input *I);
 /* src/solver.c:1143-1230.  Scales fine_flux and every f_psi/b_psi. */
 void renormalize_flux(Params params, Input I, CommGrid grid);
 /* src/solver.c:1235-1320.  Rewrites fine_source; returns the residual. */

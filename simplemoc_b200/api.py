@@ -93,7 +93,7 @@ _HOST_DTYPE = {HOST_N_SEGMENTS: np.int64, HOST_XS_INDEX: np.int32, ARR_SEG_COUNT
 
 # every symbol include/moc_b200.h declares (checked by tests/test_abi.py)
 EXPORTED = [
-    "transport_sweep", "renormalize_flux", "update_sources", "compute_keff",
+    "transport_sweep", "two_way_transport_sweep", "renormalize_flux", "update_sources", "compute_keff",
     "fast_transfer_boundary_fluxes", "moc_dropin_configure", "moc_set_device", "moc_handle_of",
     "moc_set_resident", "moc_dropin_trust_device", "moc_dropin_set_grid", "moc_sync_to_host", "moc_release",
     "moc_create", "moc_create_synthetic", "moc_destroy", "moc_set_option", "moc_get_option", "moc_sweep", "moc_two_way_sweep",
@@ -170,6 +170,8 @@ def lib():
     # drop-in names (structures by value where the reference passes them by value)
     L.transport_sweep.restype = None
     L.transport_sweep.argtypes = [C.POINTER(Params), ip]
+    L.two_way_transport_sweep.restype = None
+    L.two_way_transport_sweep.argtypes = [C.POINTER(Params), ip]
     L.renormalize_flux.restype = None
     L.renormalize_flux.argtypes = [Params, Input, CommGrid]
     L.update_sources.restype = C.c_float

@@ -285,6 +285,26 @@ extern "C" void transport_sweep(Params *params, Input *I)
     if (g_resident) m.dirty_sweep = true;
 }
 
+// solver.c:556-891: the reference compiles this sweep and calls it from nowhere (it is not in SimpleMOC_header.h either);
+// a host program that does call it finds the name here.  Plain copies around moc_two_way_sweep: everything it reads
+// (ray heights and weights, both angular-flux rows, sources, scalar flux, sigT) up, everything it writes (both
+// angular-flux rows, scalar flux, the reset ray heights) down.
+extern "C" void two_way_transport_sweep(Params *params, Input *I)
+{
+    HostLayout L;
+    Mirror &m = mirror_for(params, I, L, PART_TRACKS | PART_PSI_F | PART_PSI_B | PART_SOURCE | PART_FLUX | PART_SIGT,
+                           "two_way_transport_sweep");
+    long segs = 0;
+    if (moc_two_way_sweep(m.h, &segs)) die("two_way_transport_sweep");
+    I->segments_processed = segs;
+    if (g_resident) {
+        m.dirty_all = true;
+        return;
+    }
+    if (move_parts(m.h, L, params, PART_TRACKS | PART_PSI_F | PART_PSI_B | PART_FLUX, false)) die("two_way_transport_sweep");
+    finish(m.h, "two_way_transport_sweep");
+}
+
 extern "C" void renormalize_flux(Params params, Input I, CommGrid grid)
 {
     (void)grid;

@@ -83,3 +83,34 @@ def test_two_way_sweep_sfu_mode(built):
     assert np.quantile(rel, 0.9) <= TOL
     assert p <= TOL
     dev.close(); host.close(); oracle.close()
+
+
+def test_two_way_dropin_name_against_the_reference_own_function(built):
+    """two_way_transport_sweep under the reference's name, on the Params/Input the UNMODIFIED reference's build_tracks()
+    allocated, against the UNMODIFIED reference's own two_way_transport_sweep on a twin problem (oracle/_ref) -- on a
+    case where that function is defined (no table lookup in front of the table)."""
+    import ctypes as C
+    from oracle_lib import CASES, RefCase, frac_within, ref_available
+    if not ref_available():
+        pytest.skip("oracle/_ref did not travel")
+    L = api.lib()
+    vals, seed = CASES["polar1"], 2
+    mine, theirs = RefCase(vals, seed=seed), RefCase(vals, seed=seed)
+    L.moc_dropin_configure(seed, mine.init_rand_calls, 0, 48)
+    L.moc_set_resident(0)
+    params = api.Params.from_address(mine._ptr("params"))
+    inp = api.Input.from_address(mine._ptr("input_mut"))
+    for sweep in range(2):
+        n_cpu = theirs.two_way_sweep()                                        # the reference, on the CPU
+        L.two_way_transport_sweep(C.byref(params), C.byref(inp))              # the library, on the GPU
+        assert inp.segments_processed == n_cpu
+        assert np.array_equal(mine.z_height, theirs.z_height)
+        for name in ("fine_flux", "psi"):
+            a, b = getattr(mine, name), getattr(theirs, name)
+            assert rel_l2(a, b) <= TOL, (name, sweep)
+            assert sweep or frac_within(a, b, TOL) >= 0.999, name
+    # the one-way sweep after it: the random stream moved by one draw per forward segment on both sides
+    L.transport_sweep(C.byref(params), C.byref(inp))
+    assert inp.segments_processed == theirs.sweep()
+    assert np.array_equal(mine.z_height, theirs.z_height)
+    assert L.moc_release(C.byref(params)) == 0
