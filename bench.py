@@ -583,6 +583,17 @@ def run_moc(args):
         segs, launches = int(s[0].item()), int(s[1].item())
     integrations = segs * G
     value = integrations / (ms * 1e-3)
+    # N > 1: every rank's own sweep and attenuation time.  The step synchronises the ranks (exchange, two all-reduces),
+    # so the step time is the SLOWEST GPU's sweep plus the reductions: the spread says how much of the scaling loss is
+    # board-to-board variation under the power cap rather than communication.
+    per_rank = None
+    if dist is not None:
+        n_l = max(args.steps, 1)
+        mine = torch.tensor([state["sweep_ms"] / n_l, state["att_ms"] / n_l], dtype=torch.float64, device="cuda")
+        everyone = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(everyone, mine)
+        per_rank = {"sweep_ms": [round(float(x[0].item()), 1) for x in everyone],
+                    "attenuate_ms": [round(float(x[1].item()), 1) for x in everyone]}
 
     leakage = dev.leakage
     # ---- the same step with the other exponential (north_star: MUFU.EX2 instead of the reference's table),
@@ -666,6 +677,8 @@ def run_moc(args):
                 "cpu_baseline": cpu}
         if exchange_parity is not None:
             line["exchange_parity"] = exchange_parity
+        if per_rank is not None:
+            line["per_rank_ms"] = per_rank
         line["config"]["keff_feedback"] = ("k-eff of step n feeds update_sources of step n+1 (main.c:81,89); replaced by 1.0 when it "
                                           "leaves [1e-2, 1e2] (with neighbours the reference adds un-normalised flux sums to the "
                                           "leakage and never resets it, comms.c:120: k collapses after its single iteration)")
