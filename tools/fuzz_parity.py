@@ -86,6 +86,22 @@ while done < n_cases:
             kg, kc = dev.compute_keff(), ora.compute_keff()
             if sw == 0 and np.isfinite(kc) and abs(kg - kc) > keff_tolerance(ora, inp) * abs(kc):
                 msgs.append(f"keff {kg} vs {kc} (tolerance {keff_tolerance(ora, inp):.1e})")
+        two_way = ""
+        if rng.integers(0, 2) == 0:
+            # the reference's dead two-way sweep from the state the loop above left (solver.c:556-891): integers of both
+            # passes exact; flux where the function is defined (no table lookup in front of the table)
+            n_g, n_c2 = dev.two_way_sweep(), ora.two_way_sweep()
+            if n_g != n_c2: msgs.append(f"two-way: segments {n_g} != {n_c2}")
+            if not np.array_equal(dev.get(api.ARR_SEG_COUNT), ora.seg_count): msgs.append("two-way: seg_count")
+            if not np.array_equal(dev.get(api.ARR_QSR_DIGEST), ora.digest): msgs.append("two-way: digest")
+            if not np.array_equal(dev.get(api.ARR_QSR_DIGEST_BACK), ora.digest_back): msgs.append("two-way: backward digest")
+            if not np.array_equal(dev.get(api.ARR_Z_HEIGHT), ora.z_height): msgs.append("two-way: z_height")
+            oob = ora.table_oob
+            if oob == 0:
+                for name, a, b in (("flux", dev.get(api.ARR_FINE_FLUX), ora.fine_flux), ("psi", dev.get(api.ARR_PSI), ora.psi)):
+                    e = rel_l2(a, b)
+                    if not (e <= 1e-4): msgs.append(f"two-way: {name} rel-L2 {e:.2e}")
+            two_way = f" +two-way({'defined' if oob == 0 else str(oob) + ' lookups out of bounds'})"
         dropin = ""
         if rng.integers(0, 3) == 0:
             # the same problem through the drop-in names on HOST structures (non-resident: every call uploads
@@ -119,7 +135,7 @@ while done < n_cases:
             L.moc_release(C.byref(host2.P))
             host2.close(); ora2.close()
             dropin = f" +drop-in({chunks} chunks)"
-        status = ("ok" if not msgs else "MISMATCH " + "; ".join(msgs)) + dropin
+        status = ("ok" if not msgs else "MISMATCH " + "; ".join(msgs)) + two_way + dropin
         bad += bool(msgs)
         print(f"[{done:3d}] T2={inp.ntracks_2D} P={inp.n_polar_angles} Z={inp.z_stacked} G={inp.n_egroups} cai={cai} fai={fai} exp={axial_exp} "
               f"dax={dax} spt={vals[12]} walk={walk} segs={n_c}: {status}", flush=True)
