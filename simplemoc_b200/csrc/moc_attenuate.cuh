@@ -573,24 +573,29 @@ __device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void *src, uin
 }
 
 // shared-memory plan of attenuate_staged_kernel for G groups (host and device agree through these)
-__host__ __device__ constexpr int staged_track_stride(int G)
+__host__ __device__ constexpr int staged_track_stride(int G, int L = 8)
 {
-    // 16 G bytes per block; padded so that consecutive tracks start 32 bytes further along the banks (stride = 32
-    // mod 128): the four tracks' tail groups (8 lanes x 4 bytes each) then hit four different bank octets
-    return 16 * G + ((32 - (16 * G) % 128) + 128) % 128;
+    // 16 G bytes per block, padded against bank conflicts between the tracks of a warp.
+    // L = 8 (four tracks per warp): a quarter-warp's LDS.128 reads one track's 128 contiguous bytes; the tail groups
+    //   (8 lanes x 4 bytes per track) want consecutive tracks 32 bytes further along the banks: stride = 32 mod 128.
+    // L = 4 (eight tracks per warp): a quarter-warp's LDS.128 reads 64 bytes of each of two tracks: stride = 64 mod 128.
+    const int want = L == 8 ? 32 : 64;
+    return 16 * G + ((want - (16 * G) % 128) + 128) % 128;
 }
 __host__ __device__ constexpr int staged_table_bytes(int table_n) { return (8 * (table_n + 1) + 127) / 128 * 128; }
-__host__ __device__ constexpr int staged_smem_bytes(int G, int table_n, int warps, bool table)
+__host__ __device__ constexpr int staged_smem_bytes(int G, int table_n, int warps, bool table, int L = 8)
 {
-    return (table ? staged_table_bytes(table_n) : 0) + 128 /* mbarriers */ + warps * 2 * 4 * staged_track_stride(G);
+    return (table ? staged_table_bytes(table_n) : 0) + 128 /* mbarriers */ + warps * 2 * (32 / L) * staged_track_stride(G, L);
 }
 
-template <int NV4, int NS, int MODE, int GC>
-__global__ void __launch_bounds__(128, 4) attenuate_staged_kernel(const StagedParams sp)
+// L lanes per track (8: four tracks per warp, four CTAs per SM; 4: eight tracks per warp -- the per-segment work that
+// does not depend on the number of tracks is shared by twice as many -- two CTAs per SM with twice the registers).
+template <int L, int NV4, int NS, int MODE, int GC>
+__global__ void __launch_bounds__(128, L == 8 ? 4 : 2) attenuate_staged_kernel(const StagedParams sp)
 {
     const AttenuateParams &a = sp.a;
-    constexpr int L = 8, TPW = 4, G = GC;
-    constexpr int STRIDE = staged_track_stride(G), STAGE = TPW * STRIDE, BLOCK_BYTES = 16 * G;
+    constexpr int TPW = 32 / L, G = GC;
+    constexpr int STRIDE = staged_track_stride(G, L), STAGE = TPW * STRIDE, BLOCK_BYTES = 16 * G;
     extern __shared__ __align__(128) unsigned char s_raw[];
     constexpr bool TABLE = MODE != 2;
     const int table_bytes = TABLE ? staged_table_bytes(a.table_n) : 0;

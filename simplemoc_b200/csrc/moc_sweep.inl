@@ -205,17 +205,17 @@ static bool staged_applies(const moc_handle *h)
     return staged_smem_bytes(G, h->table_n, 4, h->exp_mode != 1) <= 227 * 1024;
 }
 
-template <int NV4, int NS, int GC>
+template <int L, int NV4, int NS, int GC>
 static int launch_staged_mode(const moc_handle *h, const StagedParams &sp, unsigned grid)
 {
     const int mode = h->exp_mode == 1 ? 2 : (h->fast_cell_ok ? 1 : 0);
-    const int smem = staged_smem_bytes(GC, h->table_n, 4, mode != 2);
+    const int smem = staged_smem_bytes(GC, h->table_n, 4, mode != 2, L);
     h->launch_count++;
 #define MOC_LAUNCH_STAGED(M)                                                                                        \
     do {                                                                                                           \
         static int smem_allowed = 0;                                                                               \
         if (smem > smem_allowed) {                                                                                 \
-            if (cudaFuncSetAttribute(attenuate_staged_kernel<NV4, NS, M, GC>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+            if (cudaFuncSetAttribute(attenuate_staged_kernel<L, NV4, NS, M, GC>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                      smem) != cudaSuccess) {                                                       \
                 moc_set_error("attenuate_staged_kernel: %d bytes of shared memory refused", smem);                 \
                 cudaGetLastError();                                                                                \
@@ -223,7 +223,7 @@ static int launch_staged_mode(const moc_handle *h, const StagedParams &sp, unsig
             }                                                                                                      \
             smem_allowed = smem;                                                                                   \
         }                                                                                                          \
-        attenuate_staged_kernel<NV4, NS, M, GC><<<grid, 128, smem, h->stream>>>(sp);                               \
+        attenuate_staged_kernel<L, NV4, NS, M, GC><<<grid, 128, smem, h->stream>>>(sp);                               \
     } while (0)
     if (mode == 0) MOC_LAUNCH_STAGED(0);
     else if (mode == 1) MOC_LAUNCH_STAGED(1);
@@ -237,13 +237,15 @@ static int launch_staged(const moc_handle *h, const AttenuateParams &a, long lon
     StagedParams sp;
     sp.a = a;
     sp.coef4 = h->d.coef4;
+    // (L = 4, eight tracks per warp, <4, 6, 2, 104>: 6.5 % fewer instructions per track-segment, but two CTAs of 255
+    // registers per SM leave two warps per scheduler -- 471 instead of 343 ms, profiles/r02_K1_lanes_ab_L4.json.)
     const unsigned grid = (unsigned)((n_tracks + 15) / 16);
     switch (h->G) {
-    case 104: return launch_staged_mode<3, 1, 104>(h, sp, grid);
-    case 100: return launch_staged_mode<3, 1, 100>(h, sp, grid);
-    case 128: return launch_staged_mode<4, 0, 128>(h, sp, grid);
-    case 64: return launch_staged_mode<2, 0, 64>(h, sp, grid);
-    case 32: return launch_staged_mode<1, 0, 32>(h, sp, grid);
+    case 104: return launch_staged_mode<8, 3, 1, 104>(h, sp, grid);
+    case 100: return launch_staged_mode<8, 3, 1, 100>(h, sp, grid);
+    case 128: return launch_staged_mode<8, 4, 0, 128>(h, sp, grid);
+    case 64: return launch_staged_mode<8, 2, 0, 64>(h, sp, grid);
+    case 32: return launch_staged_mode<8, 1, 0, 32>(h, sp, grid);
     }
     moc_set_error("no staged attenuation kernel for %d groups", h->G);
     return MOC_EINVAL;

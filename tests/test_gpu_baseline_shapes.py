@@ -107,3 +107,4 @@ def test_baseline_shape_slice_sfu_mode_integers(built, name):
     assert np.array_equal(dev.get(api.ARR_SEG_COUNT), oracle.seg_count)
     assert np.array_equal(dev.get(api.ARR_QSR_DIGEST), oracle.digest)
     dev.close(); host.close(); oracle.close()
+
