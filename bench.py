@@ -94,6 +94,10 @@ def parse_args():
                     help="N > 1: NCCL_MAX_CTAS for the boundary exchange (unless the environment already sets it)")
     ap.add_argument("--staged", type=int, default=1, choices=[0, 1],
                     help="1 (default): TMA-staged attenuation kernel; 0: the direct-gather kernel (A/B timing)")
+    ap.add_argument("--fill-overlap", type=int, default=0,
+                    help="ray-trace CTAs per SM emitting batch b+1's records under the attenuation of batch b (A/B timing; "
+                         "0: the ray trace runs in front of the attenuation)")
+    ap.add_argument("--fill-batches", type=int, default=0, help="with --fill-overlap: batches per sweep")
     return ap.parse_args()
 
 
@@ -522,6 +526,10 @@ def run_moc(args):
         dev.set_option(api.OPT_STAGED, 0)
     if not args.noclamp:
         dev.set_option(api.OPT_NOCLAMP, 0)
+    if args.fill_overlap:
+        dev.set_option(api.OPT_FILL_OVERLAP, args.fill_overlap)
+    if args.fill_batches:
+        dev.set_option(api.OPT_FILL_BATCHES, args.fill_batches)
     cx, cy, cz = grid_for(world, args.grid)
     grid = m.make_grid(cx, cy, cz, rank)
     if world > 1:
