@@ -139,6 +139,7 @@ extern "C" int moc_two_way_sweep(moc_handle *h, long *segments_processed)
                       "return from this input)", TWO_WAY_GUARD);
         return MOC_EINVAL;
     }
+    memset(&h->timing, 0, sizeof h->timing);   // no phase timers on this path
     h->timing.n_batches = n_batches;
     h->timing.launches = h->launch_count - launches_before;
     // solver.c:752, 826: only the quadratic branch counts, once per pass
