@@ -73,8 +73,17 @@ extern "C" int moc_two_way_sweep(moc_handle *h, long *segments_processed)
                              cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(cudaMemcpyAsync(h->pair_base_pinned + pairs + 1, h->d.rec_base, sizeof(unsigned long long) * (size_t)(pairs + 1),
                              cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(&h->walk_flags_host, w.flags, sizeof(unsigned int), cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     CUDA_TRY(cudaGetLastError());
+    if (h->walk_flags_host & 2u) {
+        // before any record is sized by these counts
+        h->walk_flags_host = 0;
+        CUDA_TRY(cudaMemsetAsync(w.flags, 0, sizeof(unsigned int), h->stream));
+        moc_set_error("moc_two_way_sweep: a ray made more than %d steps inside one 2D segment (the reference would not "
+                      "return from this input)", TWO_WAY_GUARD);
+        return MOC_EINVAL;
+    }
     const unsigned long long *base = h->pair_base_pinned + pairs + 1;
     const unsigned long long total = h->pair_base_pinned[pairs];
 
@@ -128,17 +137,10 @@ extern "C" int moc_two_way_sweep(moc_handle *h, long *segments_processed)
         n_batches++;
         p = q;
     }
-    CUDA_TRY(cudaMemcpyAsync(&h->walk_flags_host, w.flags, sizeof(unsigned int), cudaMemcpyDeviceToHost, h->stream));
+    h->walk_flags_host = 0;
+    CUDA_TRY(cudaMemsetAsync(w.flags, 0, sizeof(unsigned int), h->stream));   // bit 2 (a ray below the node) is informational
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     CUDA_TRY(cudaGetLastError());
-    const unsigned int flags = h->walk_flags_host;
-    h->walk_flags_host = 0;
-    CUDA_TRY(cudaMemsetAsync(w.flags, 0, sizeof(unsigned int), h->stream));
-    if (flags & 2u) {
-        moc_set_error("moc_two_way_sweep: a ray made more than %d steps inside one 2D segment (the reference would not "
-                      "return from this input)", TWO_WAY_GUARD);
-        return MOC_EINVAL;
-    }
     memset(&h->timing, 0, sizeof h->timing);   // no phase timers on this path
     h->timing.n_batches = n_batches;
     h->timing.launches = h->launch_count - launches_before;
