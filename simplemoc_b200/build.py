@@ -36,7 +36,7 @@ def _run(cmd, verbose):
 def build_lib(force=False, verbose=False, extra_nvcc=(), out=None):
     srcs = [os.path.join(CSRC, f) for f in
             ("moc_device.cu", "moc_sweep.inl", "moc_phases.inl", "moc_comm.inl", "moc_dropin.inl", "moc_kernels.cuh",
-             "moc_walk_warp.cuh", "moc_attenuate.cuh", "moc_host.c", "moc_internal.h")]
+             "moc_walk_warp.cuh", "moc_attenuate.cuh", "moc_two_way.cuh", "moc_two_way.inl", "moc_host.c", "moc_internal.h")]
     srcs += [os.path.join(INCLUDE, f) for f in ("moc_b200.h", "moc_rng.h")]
     out = out or LIB
     if not force and not _newer(out, srcs):

@@ -614,8 +614,17 @@ __device__ __forceinline__ void walk_stack_warp(const WalkParams &w, const long 
 // The grid may be smaller than the work (warps stride over the stacks): the emitting pass of batch b+1
 // runs as a few resident CTAs per SM UNDER the attenuation of batch b (sweep_core), filling the issue
 // slots that kernel leaves idle, instead of as a full grid in front of it.
+// resident CTAs per SM the walk is compiled for (0: the compiler's choice: 96 registers emitting, 78 counting).
+// Counting at 7 CTAs (72 registers, 32 bytes spilled): 11.0 instead of 11.5 ms per sweep; emitting at 6 (80 registers):
+// no change (profiles/r02_K0_launch_bounds_ab.log).
+#ifndef MOC_WALK_MIN_BLOCKS_FILL
+#define MOC_WALK_MIN_BLOCKS_FILL 0
+#endif
+#ifndef MOC_WALK_MIN_BLOCKS_COUNT
+#define MOC_WALK_MIN_BLOCKS_COUNT 7
+#endif
 template <int KPT, bool FILL, bool UP, bool FAST>
-__global__ void __launch_bounds__(128) stack_walk_warp_kernel(const WalkParams w, long long dir_before, long long n_dir)
+__global__ void __launch_bounds__(128, FILL ? MOC_WALK_MIN_BLOCKS_FILL : MOC_WALK_MIN_BLOCKS_COUNT) stack_walk_warp_kernel(const WalkParams w, long long dir_before, long long n_dir)
 {
     __shared__ uint4 scratch[4][WALK_SCRATCH_BYTES / 16];
     const int lane = threadIdx.x & 31;
